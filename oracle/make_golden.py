@@ -1,0 +1,121 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference/pyHGT/conv.py,
+model.py) on CPU behind oracle/pyg_shim.py.  TEST INFRASTRUCTURE ONLY.
+
+Run in the dev container (the reference tree does not travel to the GPU box):
+    python -m oracle.make_golden
+
+Each fixture holds: cfg (constructor args), state_dict (reference parameter names), the five input
+tensors, out [N,d], att [E,H], and — where ``grads`` is set — d(sum(out*w))/d{node_inp, params}.
+Sizes are kept to a few hundred KB each so they can be committed.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import pyg_shim                      # noqa: E402
+from pyhgt_b200 import synth                      # noqa: E402
+
+OUT_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def _perturb(module, seed):
+    """Move skip / relation_pri / LayerNorm affine / biases away from their constant inits so a
+    missing term cannot hide behind a 1 or a 0."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("skip") or name.endswith("relation_pri") or "norms" in name or "norm." in name:
+                p.add_(torch.randn(p.shape, generator=g) * 0.3)
+
+
+def conv_case(name, graph, d, heads, use_norm, use_RTE, seed, grads=False, feat_scale=1.0):
+    conv, _ = pyg_shim.load_reference()
+    torch.manual_seed(seed)
+    m = conv.HGTConv(d, d, graph.num_types, graph.num_relations, heads, 0.2, use_norm, use_RTE)
+    _perturb(m, seed + 1)
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 2)
+    x = torch.randn(graph.num_nodes, d, generator=g) * feat_scale
+    fx = {"cfg": dict(in_dim=d, out_dim=d, num_types=graph.num_types, num_relations=graph.num_relations,
+                      n_heads=heads, use_norm=use_norm, use_RTE=use_RTE),
+          "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+          "node_inp": x, "node_type": graph.node_type, "edge_index": graph.edge_index,
+          "edge_type": graph.edge_type, "edge_time": graph.edge_time}
+    if grads:
+        x = x.clone().requires_grad_(True)
+        w = torch.randn(graph.num_nodes, d, generator=g)
+        out = m(x, graph.node_type, graph.edge_index, graph.edge_type, graph.edge_time)
+        (out * w).sum().backward()
+        fx["grad_weight"] = w
+        fx["grad_node_inp"] = x.grad.detach().clone()
+        fx["grad_params"] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        fx["out"] = out.detach().clone()
+    else:
+        with torch.no_grad():
+            fx["out"] = m(x, graph.node_type, graph.edge_index, graph.edge_type, graph.edge_time).clone()
+    fx["att"] = m.att.detach().clone()
+    path = os.path.join(OUT_DIR, name + ".pt")
+    torch.save(fx, path)
+    print("%-28s N=%d E=%d d=%d H=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, d, heads,
+                                                 os.path.getsize(path) / 1024))
+
+
+def gnn_case(name, graph, in_dim, n_hid, heads, n_layers, seed):
+    """GNN.forward (model.py:69-80): per-type adapter + stack of GeneralConv('hgt')."""
+    _, model = pyg_shim.load_reference()
+    torch.manual_seed(seed)
+    m = model.GNN(in_dim, n_hid, graph.num_types, graph.num_relations, heads, n_layers, 0.2,
+                  "hgt", True, False, True)
+    _perturb(m, seed + 1)
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 2)
+    x = torch.randn(graph.num_nodes, in_dim, generator=g)
+    with torch.no_grad():
+        out = m(x, graph.node_type, graph.edge_time, graph.edge_index, graph.edge_type)
+    fx = {"cfg": dict(in_dim=in_dim, n_hid=n_hid, num_types=graph.num_types, num_relations=graph.num_relations,
+                      n_heads=heads, n_layers=n_layers, prev_norm=True, last_norm=False, use_RTE=True),
+          "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+          "node_feature": x, "node_type": graph.node_type, "edge_index": graph.edge_index,
+          "edge_type": graph.edge_type, "edge_time": graph.edge_time, "out": out.clone()}
+    path = os.path.join(OUT_DIR, name + ".pt")
+    torch.save(fx, path)
+    print("%-28s N=%d E=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, os.path.getsize(path) / 1024))
+
+
+def main():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    c1 = synth.make_c1()
+    conv_case("c1_norte", c1, 64, 4, True, False, seed=10)              # BASELINE config 1
+    conv_case("c1_rte", c1, 64, 4, True, True, seed=11, grads=True)
+    # unsorted types, all <s,t,r> triples, isolated destinations, self loops, multi-edges, d_k=4
+    g = synth.make_random(300, 2500, 3, 4, seed=21, isolated_frac=0.3, self_loops=40, duplicate_edges=60)
+    conv_case("rand_t3r4_dk4", g, 32, 8, False, True, seed=12, grads=True)
+    # odd head width (d_k = 25 -> scalar lanes) and larger feature magnitude
+    g = synth.make_random(200, 1500, 2, 3, seed=22, sorted_types=True)
+    conv_case("rand_dk25", g, 100, 4, True, False, seed=13, feat_scale=2.0)
+    # OAG head width d_k = 50 (d=100, H=2) with RTE, mag-shaped miniature (authors have no in-edges)
+    g = synth.make_mag_shaped(scale=2e-4, seed=23)
+    conv_case("mag_mini_dk50", g, 100, 2, True, True, seed=14)
+    # oag-shaped miniature, d_k = 16, 6 types / 10 relations incl. self relation
+    g = synth.make_oag_shaped(scale=2e-3, seed=24)
+    conv_case("oag_mini", g, 64, 4, True, True, seed=15)
+    # a hub: one destination receives 3000 of the edges (segment splitting), H=2
+    g = synth.make_random(400, 1000, 2, 2, seed=25)
+    hub = torch.full((3000,), 7, dtype=torch.int64)
+    gen = torch.Generator().manual_seed(99)
+    g.edge_index = torch.cat([g.edge_index, torch.stack([torch.randint(0, 400, (3000,), generator=gen), hub])], 1)
+    g.edge_type = torch.cat([g.edge_type, torch.randint(0, 2, (3000,), generator=gen)])
+    g.edge_time = torch.cat([g.edge_time, torch.randint(0, 240, (3000,), generator=gen)])
+    conv_case("hub_h2", g, 64, 2, True, True, seed=16)
+    # whole-model fixture: reference GNN (adapter + 2 HGT layers)
+    g = synth.make_random(250, 2000, 3, 3, seed=26, sorted_types=True, self_loops=250)
+    gnn_case("gnn_2layer", g, 48, 64, 4, 2, seed=17)
+
+
+if __name__ == "__main__":
+    main()
