@@ -1,0 +1,180 @@
+/* hgt_b200.h — C ABI of libhgt_b200.so: the B200 (sm_100a) implementation of pyHGT's HGTConv
+ * message-passing hot path.
+ *
+ * Boundary being replaced (reference = acbull/pyHGT, paths relative to the reference root):
+ *   pyHGT/conv.py:56-58    HGTConv.forward -> MessagePassing.propagate
+ *   pyHGT/conv.py:60-111   HGTConv.message  (typed Q/K/V projections, relation_att / relation_msg,
+ *                                           relation_pri, torch_geometric.utils.softmax by target)
+ *   pyHGT/conv.py:114-134  HGTConv.update   (gelu, typed a_linear, sigmoid(skip) gate, LayerNorm)
+ *   pyHGT/conv.py:283-299  RelTemporalEncoding
+ *   third-party: torch_geometric 1.3.2 propagate/softmax, torch_scatter 1.3.2 scatter_add/max
+ * The reference has no FFI of its own (pure Python); the Python class pyhgt_b200.HGTConv binds these
+ * entry points with ctypes (see INTEGRATION.md for the stub a pyHGT maintainer would add).
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on error; hgt_last_error() then returns a
+ *     thread-local, NUL-terminated description.  Nothing throws across the boundary.
+ *   - All pointers are DEVICE pointers unless the parameter name starts with `h_`.
+ *   - The caller owns every buffer (inputs, outputs, workspaces).  The library never allocates or frees
+ *     device memory and never synchronises the stream unless the function's comment says so.
+ *   - `stream` is a cudaStream_t passed as void* (so the header needs no CUDA include).
+ *   - Internal node order ("rank order"): nodes sorted stably by node type.  rank[n] is the position of
+ *     original node n, perm[k] the original id at position k.  All tables (Q, KV, agg) are in rank order.
+ */
+#ifndef HGT_B200_H
+#define HGT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGT_RTE_MAX_LEN 240 /* RelTemporalEncoding max_len, conv.py:287 */
+
+const char* hgt_last_error(void);
+int hgt_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph ingest: int64 COO (the tensors pyHGT/data.py:251-256 `to_torch` emits) -> plan arrays.
+ * Replaces PyG propagate's per-layer index_select gathers and the T*T*R boolean triple masks
+ * (conv.py:71-84) with one destination-sorted CSR built once per graph.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch needed by hgt_plan_nodes / hgt_plan_edges_sort / hgt_plan_tiles. */
+int hgt_plan_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* out_bytes);
+
+/* Stable sort of nodes by type.  rank/perm: [N] int32.  type_count: [T+1] int32 (bucket T collects nodes
+ * whose type is outside [0,T): the reference leaves their output rows zero, conv.py:120-124).
+ * sorted_flag[0] = 1 if node_type was already non-decreasing (then rank = perm = identity). */
+int hgt_plan_nodes(const int64_t* node_type, int64_t n_nodes, int32_t num_types,
+                   int32_t* rank, int32_t* perm, int32_t* type_count, int32_t* sorted_flag,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sort edges by destination rank (stable in original edge order).
+ *   edge_index [2,E] int64 row-major (row 0 = source j, row 1 = target i; data.py:245,254)
+ *   row_ptr [N+1] int32, csr_eid [E] int32 (CSR position -> original edge id),
+ *   presence [T*R] int32: 1 where some valid edge has <source_type, relation> (the "pairs"),
+ *   flags [4] int32: flags[0] != 0 => an endpoint id was outside [0,N). */
+int hgt_plan_edges_sort(const int64_t* edge_index, const int64_t* edge_type, const int64_t* node_type,
+                        const int32_t* rank, int64_t n_nodes, int64_t n_edges,
+                        int32_t num_types, int32_t num_relations,
+                        int32_t* row_ptr, int32_t* csr_eid, int32_t* presence, int32_t* flags,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-CSR-edge gather indices.
+ *   pair_of [T*R] int32: pair id of <source_type, relation> or -1;  pair_row0 [P] int32: first KV-table
+ *   row of each pair;  type_row0 [T+1] int32: first rank of each type;  zero_row: index of the all-zero
+ *   KV row used for edges that match no triple (score 0, message 0: conv.py:68-69).
+ *   kv_row [E] int32;  rte_row [E] int32 (pair*240 + dt, or zero_rte_row) — pass NULL when edge_time is
+ *   NULL.  flags[1] != 0 => an edge_time was outside [0,240) (nn.Embedding would raise, conv.py:299). */
+int hgt_plan_edges_fill(const int64_t* edge_index, const int64_t* edge_type, const int64_t* edge_time,
+                        const int64_t* node_type, const int32_t* rank, const int32_t* csr_eid,
+                        int64_t n_nodes, int64_t n_edges, int32_t num_types, int32_t num_relations,
+                        const int32_t* pair_of, const int32_t* pair_row0, const int32_t* type_row0,
+                        int32_t zero_row, int32_t zero_rte_row,
+                        int32_t* kv_row, int32_t* rte_row, int32_t* flags, void* stream);
+
+/* Balanced work tiles for the edge kernel: consecutive destination ranks are grouped until a tile holds
+ * about `target_edges` edges; a destination with more than `split_edges` in-edges is cut into several
+ * tiles whose partial (max, sum, acc) are merged afterwards.
+ *   tiles [max_tiles,4] int32 = {dst_begin, dst_end, edge_begin, edge_end}; for a split destination
+ *   the second field is -(partial_slot+1) < 0 and [edge_begin, edge_end) is a sub-range of its segment.
+ *   n_tiles [2] int32 = {number of tiles, number of split (partial) tiles}.
+ * Synchronises the stream (returns the counts to the host through h_n_tiles[2]). */
+int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges,
+                   int32_t target_edges, int32_t split_edges,
+                   int32_t* tiles, int64_t max_tiles, int32_t* d_n_tiles, int32_t* h_n_tiles,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[k,:] = in[perm[k],:]  (rows of `width` floats); used only when node_type is not pre-sorted. */
+int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_rows, int32_t width,
+                    float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Typed (per-node-type) linear layers — "per-type linear dispatch" (conv.py:73-77,96-97,103,125).
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int64_t a_row0;    /* first row of A used by this group                                   */
+  int64_t m;         /* rows in this group (nodes of this type; 240 for the RTE tables)      */
+  int32_t w_row0;    /* first row of the concatenated weight matrix W [sum n_out, K]         */
+  int32_t n_cblocks; /* output column blocks of width `cb_width` each                        */
+  int32_t cb_first;  /* index of this group's first entry in the column-block table          */
+  int32_t has_bias;
+} hgt_lin_group;
+
+typedef struct {
+  int64_t out_off;   /* element offset of (group row 0, column 0 of this block) from `out`   */
+  int64_t ld;        /* elements between consecutive rows of this block's destination        */
+} hgt_lin_cblock;
+
+/* Fold the relation matrices into per-<source type, relation> weights:
+ *   W_cat rows for type t: [ W_q^t ; for each pair p=(t,r): K'_p ; V'_p ]  with
+ *   K'_p[h*dk+c,:] = pri[r,h]/sqrt(dk) * sum_a att[r,h,a,c] * W_k^t[h*dk+a,:]   (conv.py:97-99)
+ *   V'_p[h*dk+c,:] =                     sum_a msg[r,h,a,c] * W_v^t[h*dk+a,:]   (conv.py:103-104)
+ * and the same for the biases.  wq/wk/wv/bq/bk/bv are DEVICE arrays of T device pointers (one
+ * nn.Linear per type, conv.py:34-38).  pair_type/pair_rel: [P] int32; cat_row0: [P] int32 first W_cat
+ * row of the pair's K' block (V' follows at +d_out); q_row0: [T] int32 first W_cat row of W_q^t. */
+int hgt_fold_weights(const float* const* wq, const float* const* bq,
+                     const float* const* wk, const float* const* bk,
+                     const float* const* wv, const float* const* bv,
+                     const float* relation_att, const float* relation_msg, const float* relation_pri,
+                     int32_t num_types, int32_t num_relations, int32_t n_heads, int32_t d_in, int32_t d_out,
+                     int32_t n_pairs, const int32_t* pair_type, const int32_t* pair_rel,
+                     const int32_t* cat_row0, const int32_t* q_row0,
+                     float* w_cat, float* b_cat, void* stream);
+
+/* Concatenate T per-type [rows,cols] matrices (and [rows] biases) into one: w_cat [T*rows, cols]. */
+int hgt_concat_linears(const float* const* w, const float* const* b, int32_t num_types,
+                       int32_t rows, int32_t cols, float* w_cat, float* b_cat, void* stream);
+
+/* RelTemporalEncoding (conv.py:299) needs no entry point of its own: RT = emb.weight @ lin.weight^T + lin.bias
+ * [240,d] is one hgt_typed_linear call, and its projection through every pair's K'/V' weights another. */
+
+/* out[cblock c of group g][m, n] = sum_k A[a_row0_g + m, k] * W[w_row0_g + c*cb_width + n, k] (+ bias).
+ * fp32 in / fp32 out.  `impl`: 0 = auto, 1 = SIMT fp32 FMA kernel, 2 = tcgen05 split-bf16 tensor-core
+ * kernel (fp32-accurate to ~2^-16).  groups/cblocks are DEVICE arrays; h_groups is the same table on
+ * the host (used to size the grid; no device read-back). */
+int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* bias, int32_t K,
+                     int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
+                     int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, int32_t impl,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused edge kernel: gather -> relation-specific score -> softmax by destination -> weighted sum
+ * (conv.py:99,108-111 + PyG scatter-add), one pass over the destination-sorted CSR.
+ * ---------------------------------------------------------------------------------------------- */
+
+/*  q       [N, d]        rank order, Q[i] = W_q^{type(i)} x_i + b
+ *  kv      [rows+1, 2d]  row = [K' | V'] of <source node, relation>; last row all zero
+ *  kvr     [P*240+1, 2d] RTE contribution per <pair, dt> (NULL when !use_RTE); last row all zero
+ *  tiles   from hgt_plan_tiles;  partial workspace: n_split * (2*H + d) floats
+ *  agg_out [N, d]  gelu(sum_e att[e] * V'[e]) if apply_gelu else the raw sum   (conv.py:119)
+ *  att_out [E, H]  softmax weights in ORIGINAL edge order (conv.py:108 `self.att`) or NULL
+ *  stats_out [N, 2H] per-destination (max, sum) per head, or NULL (kept for the backward pass)
+ *  variant: 0 = auto, 1 = direct register gather (LDG), 2 = bulk-async-copy shared-memory ring (TMA) */
+int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_t n_heads, size_t* out_bytes);
+int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
+                     const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
+                     const int32_t* csr_eid, const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles,
+                     int64_t n_nodes, int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu,
+                     float* agg_out, float* att_out, float* stats_out,
+                     void* workspace, size_t workspace_bytes, int32_t variant, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Update epilogue (conv.py:129-133): y = o*sigmoid(skip[t]) + x*(1-sigmoid(skip[t])); LayerNorm_t(y)
+ * (eps 1e-5, affine) iff use_norm; rows of out-of-range type are written as zeros (conv.py:120).
+ *   o [N,d] rank order (a_linear output, after dropout if training);  x [N,d] rank order;
+ *   type_row0 [T+2] int32 prefix of type_count;  norm_w/norm_b [T,d] or NULL;  perm NULL if identity;
+ *   out [N,d] in ORIGINAL node order.
+ * ---------------------------------------------------------------------------------------------- */
+int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
+                        const float* skip, const float* norm_w, const float* norm_b,
+                        const int32_t* perm, int64_t n_nodes, int32_t d, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGT_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of libhgt_b200.so (C ABI declared in include/hgt_b200.h).
+
+The library is built in-tree by ``pyhgt_b200/build.py`` (nvcc, sm_100a).  There is NO fallback: if the
+shared object is missing or a symbol is absent, loading raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhgt_b200.so")
+
+_c = ctypes
+_p = _c.c_void_p
+_i32 = _c.c_int32
+_i64 = _c.c_int64
+_sz = _c.c_size_t
+
+# name -> argtypes; every function returns int except where noted.  Mirrors include/hgt_b200.h.
+SIGNATURES = {
+    "hgt_abi_version": [],
+    "hgt_plan_workspace_bytes": [_i64, _i64, _c.POINTER(_sz)],
+    "hgt_plan_nodes": [_p, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p],
+    "hgt_plan_edges_sort": [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p],
+    "hgt_plan_edges_fill": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p],
+    "hgt_plan_tiles": [_p, _i64, _i64, _i32, _i32, _p, _i64, _p, _c.POINTER(_i32), _p, _sz, _p],
+    "hgt_gather_rows": [_p, _p, _i64, _i32, _p, _p],
+    "hgt_fold_weights": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+                         _p, _p, _p],
+    "hgt_concat_linears": [_p, _p, _i32, _i32, _i32, _p, _p, _p],
+    "hgt_typed_linear": [_p, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p],
+    "hgt_edge_workspace_bytes": [_i32, _i32, _i32, _c.POINTER(_sz)],
+    "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p, _p,
+                         _p, _sz, _i32, _p],
+    "hgt_update_epilogue": [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p],
+}
+
+LIN_GROUP_DTYPE = np.dtype([("a_row0", "<i8"), ("m", "<i8"), ("w_row0", "<i4"), ("n_cblocks", "<i4"),
+                            ("cb_first", "<i4"), ("has_bias", "<i4")])
+LIN_CBLOCK_DTYPE = np.dtype([("out_off", "<i8"), ("ld", "<i8")])
+assert LIN_GROUP_DTYPE.itemsize == 32 and LIN_CBLOCK_DTYPE.itemsize == 16
+
+_lib = None
+
+
+class HgtError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once and attach argtypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HgtError("libhgt_b200.so not found at %s — run `python -m pyhgt_b200.build` "
+                       "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.hgt_last_error.restype = _c.c_char_p
+    lib.hgt_last_error.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
+        fn.restype = _c.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hgt_last_error()
+        raise HgtError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, or None."""
+    return None if t is None else t.data_ptr()

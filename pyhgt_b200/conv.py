@@ -1,0 +1,271 @@
+"""Drop-in replacements for pyHGT's conv layer classes (reference: pyHGT/conv.py).
+
+``HGTConv`` keeps the reference's constructor (conv.py:12), five-argument ``forward`` (conv.py:56),
+public attributes (conv.py:15-25), ``.att`` side effect (conv.py:108), ``__repr__`` (conv.py:136-139) and
+parameter / state_dict names (conv.py:28-54), but computes through the hand-written sm_100a kernels
+behind the C ABI in include/hgt_b200.h:
+
+    plan (once per graph)            hgt_plan_*          CSR by destination, pairs, gather rows, tiles
+    fold relation matrices           hgt_fold_weights    relation_att/msg/pri -> per-<type,relation> W'
+    typed projections                hgt_typed_linear    Q [N,d] and [K'|V'] tables (+ RTE tables)
+    fused edge kernel                hgt_edge_forward    score -> softmax by destination -> weighted sum (+gelu)
+    typed output linear              hgt_typed_linear    a_linears
+    gated skip + LayerNorm           hgt_update_epilogue
+
+There is no CPU path: CPU tensors raise.  ``GeneralConv`` mirrors conv.py:303-323 so that pyHGT's
+model.py (``from .conv import *``) runs unchanged on top of this module.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import plan as _plan
+
+
+def glorot(tensor):
+    """torch_geometric.nn.inits.glorot (used at conv.py:53-54)."""
+    if tensor is not None:
+        a = math.sqrt(6.0 / (tensor.size(-2) + tensor.size(-1)))
+        tensor.data.uniform_(-a, a)
+
+
+class RelTemporalEncoding(nn.Module):
+    """Sinusoid table + linear (reference conv.py:283-299).  Same parameter names (emb.weight,
+    lin.weight, lin.bias).  Inside HGTConv the table is never applied per edge: RT = lin(emb.weight)
+    [240,d] is projected once per <source type, relation> and added per edge by the edge kernel."""
+
+    def __init__(self, n_hid, max_len=240, dropout=0.2):
+        super().__init__()
+        position = torch.arange(0., max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, n_hid, 2) * -(math.log(10000.0) / n_hid))
+        emb = nn.Embedding(max_len, n_hid)
+        emb.weight.data[:, 0::2] = torch.sin(position * div_term) / math.sqrt(n_hid)
+        emb.weight.data[:, 1::2] = torch.cos(position * div_term) / math.sqrt(n_hid)
+        emb.requires_grad = False        # (sic) the reference sets a module attribute: the table stays trainable
+        self.emb = emb
+        self.lin = nn.Linear(n_hid, n_hid)
+
+    def forward(self, x, t):
+        return x + self.lin(self.emb(t))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _PointerTable:
+    """Device array of per-type parameter pointers, rebuilt only when a parameter moves."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+
+    def get(self, tensors, device):
+        key = tuple(t.data_ptr() for t in tensors) + (str(device),)
+        if key != self.key:
+            self.dev = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(device)
+            self.key = key
+        return self.dev
+
+
+class HGTConv(nn.Module):
+    # Class-level switches (kept out of the constructor so the reference's positional call at
+    # conv.py:308 stays valid).
+    keep_att = True            # materialise self.att [E,H] like the reference (conv.py:108)
+    edge_variant = 0           # 0 auto, 1 register gather, 2 bulk-copy ring (see csrc/edge.cu)
+    linear_impl = 0            # 0 auto, 1 fp32 SIMT, 2 tcgen05
+
+    def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
+                 use_RTE=True, **kwargs):
+        super().__init__()
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.num_types = num_types
+        self.num_relations = num_relations
+        self.total_rel = num_types * num_relations * num_types
+        self.n_heads = n_heads
+        self.d_k = out_dim // n_heads
+        self.sqrt_dk = math.sqrt(self.d_k)
+        self.use_norm = use_norm
+        self.use_RTE = use_RTE
+        self.att = None
+
+        self.k_linears = nn.ModuleList()
+        self.q_linears = nn.ModuleList()
+        self.v_linears = nn.ModuleList()
+        self.a_linears = nn.ModuleList()
+        self.norms = nn.ModuleList()
+        for _ in range(num_types):
+            self.k_linears.append(nn.Linear(in_dim, out_dim))
+            self.q_linears.append(nn.Linear(in_dim, out_dim))
+            self.v_linears.append(nn.Linear(in_dim, out_dim))
+            self.a_linears.append(nn.Linear(out_dim, out_dim))
+            if use_norm:
+                self.norms.append(nn.LayerNorm(out_dim))
+        self.relation_pri = nn.Parameter(torch.ones(num_relations, self.n_heads))
+        self.relation_att = nn.Parameter(torch.Tensor(num_relations, n_heads, self.d_k, self.d_k))
+        self.relation_msg = nn.Parameter(torch.Tensor(num_relations, n_heads, self.d_k, self.d_k))
+        self.skip = nn.Parameter(torch.ones(num_types))
+        self.drop = nn.Dropout(dropout)
+        if self.use_RTE:
+            self.emb = RelTemporalEncoding(in_dim)
+        glorot(self.relation_att)
+        glorot(self.relation_msg)
+        self._ptr_tables = {}
+
+    def __repr__(self):
+        return '{}(in_dim={}, out_dim={}, num_types={}, num_types={})'.format(
+            self.__class__.__name__, self.in_dim, self.out_dim, self.num_types, self.num_relations)
+
+    # ------------------------------------------------------------------------------------------
+    def _ptrs(self, name, tensors, device):
+        tab = self._ptr_tables.get(name)
+        if tab is None:
+            tab = self._ptr_tables[name] = _PointerTable()
+        return tab.get(tensors, device)
+
+    def _check_inputs(self, node_inp, edge_time):
+        if node_inp.device.type != "cuda":
+            raise _lib.HgtError("pyhgt_b200.HGTConv runs on CUDA tensors only (got %s): there is no CPU "
+                                "fallback" % node_inp.device)
+        if node_inp.dtype != torch.float32:
+            raise ValueError("node_inp must be float32 (the reference is fp32 throughout), got %s" % node_inp.dtype)
+        if node_inp.dim() != 2 or node_inp.shape[1] != self.in_dim:
+            raise ValueError("node_inp must be [N, %d], got %s" % (self.in_dim, tuple(node_inp.shape)))
+        if self.in_dim != self.out_dim:
+            # conv.py:131 adds node_inp to the out_dim-wide transform: the reference itself needs in == out
+            raise ValueError("HGTConv needs in_dim == out_dim for the skip connection (conv.py:131)")
+        if self.use_RTE and edge_time is None:
+            raise ValueError("use_RTE=True needs edge_time (conv.py:91-92)")
+        if self.out_dim % self.n_heads != 0:
+            raise ValueError("out_dim=%d is not divisible by n_heads=%d" % (self.out_dim, self.n_heads))
+
+    def forward(self, node_inp, node_type, edge_index, edge_type, edge_time=None):
+        self._check_inputs(node_inp, edge_time)
+        if torch.is_grad_enabled() and (node_inp.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import hgt_conv_autograd
+            return hgt_conv_autograd(self, node_inp, node_type, edge_index, edge_type, edge_time)
+        out, att, _ = self._forward_impl(node_inp, node_type, edge_index, edge_type, edge_time,
+                                         want_att=self.keep_att, save=False)
+        self.att = att
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save):
+        dev = node_inp.device
+        d_in, d = self.in_dim, self.out_dim
+        H, T, R = self.n_heads, self.num_types, self.num_relations
+        st = _stream()
+        plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if self.use_RTE else None, T, R)
+        N, E, P = plan.n_nodes, plan.n_edges, plan.n_pairs
+        if node_inp.shape[0] != N:
+            raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
+        lt = _plan.layer_tables(plan, d_in, d)
+        f32 = dict(dtype=torch.float32, device=dev)
+        x = node_inp.contiguous()
+        if plan.sorted_types:
+            x_sorted = x
+        else:
+            x_sorted = torch.empty_like(x)
+            _lib.call("hgt_gather_rows", x.data_ptr(), plan.perm.data_ptr(), N, d_in, x_sorted.data_ptr(), st)
+
+        # 1. fold relation matrices into the typed K/V weights
+        w_cat = torch.empty((max(lt.cat_rows, 1), d_in), **f32)
+        b_cat = torch.empty(max(lt.cat_rows, 1), **f32)
+        wq = self._ptrs("wq", [l.weight for l in self.q_linears], dev)
+        bq = self._ptrs("bq", [l.bias for l in self.q_linears], dev)
+        wk = self._ptrs("wk", [l.weight for l in self.k_linears], dev)
+        bk = self._ptrs("bk", [l.bias for l in self.k_linears], dev)
+        wv = self._ptrs("wv", [l.weight for l in self.v_linears], dev)
+        bv = self._ptrs("bv", [l.bias for l in self.v_linears], dev)
+        _lib.call("hgt_fold_weights", wq.data_ptr(), bq.data_ptr(), wk.data_ptr(), bk.data_ptr(), wv.data_ptr(),
+                  bv.data_ptr(), self.relation_att.data_ptr(), self.relation_msg.data_ptr(),
+                  self.relation_pri.data_ptr(), T, R, H, d_in, d, P, plan.pair_type_dev.data_ptr(),
+                  plan.pair_rel_dev.data_ptr(), lt.cat_row0_dev.data_ptr(), lt.q_row0_dev.data_ptr(),
+                  w_cat.data_ptr(), b_cat.data_ptr(), st)
+
+        # 2. typed projections: Q [N,d] and the folded [K'|V'] table (+ trailing all-zero row)
+        proj = torch.empty(lt.proj_elems, **f32)
+        q_tab = proj[lt.q_off:lt.q_off + N * d]
+        kv_tab = proj[lt.kv_off:]
+        kv_tab[plan.kv_rows * 2 * d:].zero_()
+        g_dev, g_host, n_g, c_dev = lt.proj_groups
+        _lib.call("hgt_typed_linear", x_sorted.data_ptr(), d_in, w_cat.data_ptr(), b_cat.data_ptr(), d_in, d,
+                  g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(), proj.data_ptr(), self.linear_impl, st)
+        kvr = None
+        if self.use_RTE:
+            # RT = lin(emb.weight) [240,d] (conv.py:299), then projected with every pair's K'/V' weights (no bias)
+            rt = torch.empty((_plan.RTE_MAX_LEN, d_in), **f32)
+            one_g = lt.rt_group
+            _lib.call("hgt_typed_linear", self.emb.emb.weight.data_ptr(), d_in, self.emb.lin.weight.data_ptr(),
+                      self.emb.lin.bias.data_ptr(), d_in, d_in, one_g[0].data_ptr(), one_g[1].ctypes.data, 1,
+                      one_g[3].data_ptr(), rt.data_ptr(), 1, st)
+            kvr = torch.empty((P * _plan.RTE_MAX_LEN + 1) * 2 * d, **f32)
+            kvr[P * _plan.RTE_MAX_LEN * 2 * d:].zero_()
+            g2, g2h, n_g2, c2 = lt.rte_groups
+            _lib.call("hgt_typed_linear", rt.data_ptr(), d_in, w_cat.data_ptr(), None, d_in, d, g2.data_ptr(),
+                      g2h.ctypes.data, n_g2, c2.data_ptr(), kvr.data_ptr(), 1, st)
+
+        # 3. fused edge kernel -> gelu(aggregate)
+        ws_bytes = ctypes.c_size_t()
+        _lib.call("hgt_edge_workspace_bytes", plan.n_split, d, H, ctypes.byref(ws_bytes))
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        g_act = torch.empty((N, d), **f32)
+        att = torch.empty((E, H), **f32) if want_att else None
+        stats = torch.empty((N, 2 * H), **f32) if save else None
+        _lib.call("hgt_edge_forward", q_tab.data_ptr(), kv_tab.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
+                  plan.kv_row.data_ptr(), _lib.ptr(plan.rte_row) if self.use_RTE else None,
+                  plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, N, E, d, H,
+                  0 if save else 1, g_act.data_ptr(), _lib.ptr(att), _lib.ptr(stats), ws.data_ptr(), ws.numel(),
+                  self.edge_variant, st)
+
+        # 4. typed output linear (conv.py:125) + gated skip + LayerNorm (conv.py:129-133)
+        agg = None
+        if save:
+            agg = g_act
+            g_act = F.gelu(agg)
+        wa_cat = torch.empty((T * d, d), **f32)
+        ba_cat = torch.empty(T * d, **f32)
+        wa = self._ptrs("wa", [l.weight for l in self.a_linears], dev)
+        ba = self._ptrs("ba", [l.bias for l in self.a_linears], dev)
+        _lib.call("hgt_concat_linears", wa.data_ptr(), ba.data_ptr(), T, d, d, wa_cat.data_ptr(), ba_cat.data_ptr(), st)
+        o = torch.empty((N, d), **f32)
+        g3, g3h, n_g3, c3 = lt.upd_groups
+        _lib.call("hgt_typed_linear", g_act.data_ptr(), d, wa_cat.data_ptr(), ba_cat.data_ptr(), d, d, g3.data_ptr(),
+                  g3h.ctypes.data, n_g3, c3.data_ptr(), o.data_ptr(), self.linear_impl, st)
+        if self.training and self.drop.p > 0:
+            o = self.drop(o)                                       # conv.py:125 (train mode only)
+        norm_w = norm_b = None
+        if self.use_norm:
+            norm_w = torch.stack([n.weight for n in self.norms]).contiguous()
+            norm_b = torch.stack([n.bias for n in self.norms]).contiguous()
+        out = torch.empty((N, d), **f32)
+        _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
+                  self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
+                  None if plan.sorted_types else plan.perm.data_ptr(), N, d, out.data_ptr(), st)
+        saved = None
+        if save:
+            saved = dict(plan=plan, lt=lt, x_sorted=x_sorted, w_cat=w_cat, proj=proj, kvr=kvr, agg=agg, o=o,
+                         stats=stats)
+        return out, att, saved
+
+
+class GeneralConv(nn.Module):
+    """String-keyed dispatch, reference conv.py:303-323.  'hgt' resolves to the CUDA HGTConv above;
+    the other convolution kinds are not on the hot path and raise."""
+
+    def __init__(self, conv_name, in_hid, out_hid, num_types, num_relations, n_heads, dropout, use_norm=True,
+                 use_RTE=True):
+        super().__init__()
+        self.conv_name = conv_name
+        if self.conv_name == 'hgt':
+            self.base_conv = HGTConv(in_hid, out_hid, num_types, num_relations, n_heads, dropout, use_norm, use_RTE)
+        else:
+            raise NotImplementedError("pyhgt_b200 implements conv_name='hgt' only (got %r)" % conv_name)
+
+    def forward(self, meta_xs, node_type, edge_index, edge_type, edge_time):
+        return self.base_conv(meta_xs, node_type, edge_index, edge_type, edge_time)

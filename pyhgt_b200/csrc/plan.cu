@@ -1,0 +1,360 @@
+// Graph ingest for the HGTConv hot path: int64 COO (pyHGT/data.py:251-256) -> type-sorted node order,
+// destination-sorted CSR, per-edge gather rows, balanced work tiles.  Runs once per graph; the sort
+// and scans use CUB device primitives (CUDA toolkit), everything else is hand-written.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int bits_for(int64_t n) {
+  int b = 1;
+  while ((int64_t(1) << b) < n && b < 31) ++b;
+  return b;
+}
+
+struct PlanScratch {
+  int32_t* keys_in;
+  int32_t* keys_out;
+  int32_t* vals_in;
+  int32_t* counts;   // [N+1]
+  int64_t* packed;   // [N+1] (tile planning)
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+size_t cub_sort_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 32);
+  return bytes;
+}
+size_t cub_scan_bytes(int64_t n) {
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b1, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, (const int64_t*)nullptr, (int64_t*)nullptr, (int)n);
+  return b1 > b2 ? b1 : b2;
+}
+
+size_t carve(PlanScratch& s, void* base, int64_t n_nodes, int64_t n_edges) {
+  int64_t m = n_nodes > n_edges ? n_nodes : n_edges;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += hgt_align_up(bytes, 256);
+    return base ? (char*)base + o : (char*)nullptr;
+  };
+  s.keys_in = (int32_t*)take(sizeof(int32_t) * (m + 1));
+  s.keys_out = (int32_t*)take(sizeof(int32_t) * (m + 1));
+  s.vals_in = (int32_t*)take(sizeof(int32_t) * (m + 1));
+  s.counts = (int32_t*)take(sizeof(int32_t) * (n_nodes + 2));
+  s.packed = (int64_t*)take(sizeof(int64_t) * (n_nodes + 2));
+  size_t a = cub_sort_bytes(m + 1), b = cub_scan_bytes(n_nodes + 2);
+  s.cub_bytes = a > b ? a : b;
+  s.cub_tmp = take(s.cub_bytes);
+  return off;
+}
+
+// ---- nodes -------------------------------------------------------------------------------------
+__global__ void k_node_keys(const int64_t* __restrict__ node_type, int64_t n, int T,
+                            int32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                            int32_t* __restrict__ type_count, int32_t* __restrict__ sorted_flag) {
+  extern __shared__ int32_t hist[];
+  for (int i = threadIdx.x; i <= T; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    int64_t t = node_type[i];
+    int32_t k = (t >= 0 && t < T) ? (int32_t)t : T;
+    keys[i] = k;
+    vals[i] = (int32_t)i;
+    atomicAdd(&hist[k], 1);
+    if (i + 1 < n) {
+      int64_t t2 = node_type[i + 1];
+      int32_t k2 = (t2 >= 0 && t2 < T) ? (int32_t)t2 : T;
+      if (k2 < k) *sorted_flag = 0;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j <= T; j += blockDim.x)
+    if (hist[j]) atomicAdd(&type_count[j], hist[j]);
+}
+
+__global__ void k_inverse_perm(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ rank) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) rank[perm[i]] = (int32_t)i;
+}
+
+// ---- edges -------------------------------------------------------------------------------------
+__global__ void k_edge_keys(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
+                            const int64_t* __restrict__ node_type, const int32_t* __restrict__ rank,
+                            int64_t N, int64_t E, int T, int R, int32_t* __restrict__ keys,
+                            int32_t* __restrict__ vals, int32_t* __restrict__ counts,
+                            int32_t* __restrict__ presence, int32_t* __restrict__ flags) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t src = edge_index[e], dst = edge_index[E + e];
+  vals[e] = (int32_t)e;
+  if (src < 0 || src >= N || dst < 0 || dst >= N) {
+    flags[0] = 1;
+    keys[e] = 0;
+    return;
+  }
+  int32_t key = rank[dst];
+  keys[e] = key;
+  atomicAdd(&counts[key], 1);
+  int64_t s = node_type[src], t = node_type[dst], r = edge_type[e];
+  if (s >= 0 && s < T && t >= 0 && t < T && r >= 0 && r < R) presence[s * R + r] = 1;
+}
+
+__global__ void k_edge_fill(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
+                            const int64_t* __restrict__ edge_time, const int64_t* __restrict__ node_type,
+                            const int32_t* __restrict__ rank, const int32_t* __restrict__ csr_eid,
+                            int64_t N, int64_t E, int T, int R, const int32_t* __restrict__ pair_of,
+                            const int32_t* __restrict__ pair_row0, const int32_t* __restrict__ type_row0,
+                            int32_t zero_row, int32_t zero_rte_row, int32_t* __restrict__ kv_row,
+                            int32_t* __restrict__ rte_row, int32_t* __restrict__ flags) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  int64_t e = csr_eid[c];
+  int64_t src = edge_index[e], dst = edge_index[E + e];
+  int32_t row = zero_row, rrow = zero_rte_row;
+  if (src >= 0 && src < N && dst >= 0 && dst < N) {
+    int64_t s = node_type[src], t = node_type[dst], r = edge_type[e];
+    if (s >= 0 && s < T && t >= 0 && t < T && r >= 0 && r < R) {
+      int32_t p = pair_of[s * R + r];
+      if (p >= 0) {
+        row = pair_row0[p] + (rank[src] - type_row0[s]);
+        if (edge_time) {
+          int64_t dt = edge_time[e];
+          if (dt < 0 || dt >= HGT_RTE_MAX_LEN) {
+            flags[1] = 1;   // nn.Embedding would raise (conv.py:299)
+            dt = 0;
+          }
+          rrow = p * HGT_RTE_MAX_LEN + (int32_t)dt;
+        }
+      }
+    }
+  }
+  kv_row[c] = row;
+  if (rte_row) rte_row[c] = rrow;
+}
+
+// ---- work tiles --------------------------------------------------------------------------------
+// cost(k) = 2*deg(k) + 1 (an edge reads a 2d-float KV row, every destination writes a d-float row).
+// A destination starts a tile when its cost prefix enters a new bucket of `tc` units; a hub
+// (deg > split) gets ceil(deg/split) tiles of its own.
+__device__ __forceinline__ bool tile_starts_at(const int32_t* row_ptr, int64_t k, int tc, int split) {
+  if (k == 0) return true;
+  int32_t deg_prev = row_ptr[k] - row_ptr[k - 1];
+  if (deg_prev > split) return true;                       // first destination after a hub
+  int64_t c1 = 2 * (int64_t)row_ptr[k] + k, c0 = 2 * (int64_t)row_ptr[k - 1] + (k - 1);
+  return (c1 / tc) != (c0 / tc);
+}
+
+__global__ void k_tile_emit_counts(const int32_t* __restrict__ row_ptr, int64_t N, int tc, int split,
+                                   int64_t* __restrict__ packed) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k > N) return;
+  if (k == N) { packed[k] = 0; return; }
+  int32_t deg = row_ptr[k + 1] - row_ptr[k];
+  int64_t emit, emit_split;
+  if (deg > split) {
+    emit = (deg + split - 1) / split;
+    emit_split = emit;
+  } else {
+    emit = tile_starts_at(row_ptr, k, tc, split) ? 1 : 0;
+    emit_split = 0;
+  }
+  packed[k] = (emit << 32) | emit_split;
+}
+
+__global__ void k_tile_write(const int32_t* __restrict__ row_ptr, int64_t N, int tc, int split,
+                             const int64_t* __restrict__ packed_scan, int32_t* __restrict__ tiles,
+                             int64_t max_tiles, int32_t* __restrict__ n_tiles) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k > N) return;
+  int64_t slot = packed_scan[k] >> 32, pslot = packed_scan[k] & 0xffffffffll;
+  if (k == N) { n_tiles[0] = (int32_t)slot; n_tiles[1] = (int32_t)pslot; return; }
+  int32_t b = row_ptr[k], deg = row_ptr[k + 1] - b;
+  if (deg > split) {
+    int pieces = (deg + split - 1) / split;
+    int per = (deg + pieces - 1) / pieces;
+    for (int i = 0; i < pieces; ++i) {
+      if (slot + i >= max_tiles) return;
+      int32_t* t = tiles + 4 * (slot + i);
+      int32_t eb = b + i * per, ee = min(b + deg, eb + per);
+      t[0] = (int32_t)k; t[1] = -(int32_t)(pslot + i) - 1; t[2] = eb; t[3] = ee;
+    }
+  } else if (tile_starts_at(row_ptr, k, tc, split)) {
+    if (slot >= max_tiles) return;
+    int32_t* t = tiles + 4 * slot;
+    t[0] = (int32_t)k; t[1] = 0; t[2] = b; t[3] = 0;     // end fields patched by k_tile_close
+  }
+}
+
+__global__ void k_tile_close(const int32_t* __restrict__ row_ptr, int64_t N, int32_t* __restrict__ tiles,
+                             const int32_t* __restrict__ n_tiles) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int nt = n_tiles[0];
+  if (i >= nt) return;
+  int32_t* t = tiles + 4 * i;
+  if (t[1] < 0) return;                                   // hub piece: complete
+  int32_t dend = (i + 1 < nt) ? tiles[4 * (i + 1)] : (int32_t)N;
+  t[1] = dend;
+  t[3] = row_ptr[dend];
+}
+
+__global__ void k_gather_rows(const float4* __restrict__ in, const int32_t* __restrict__ perm, int64_t n_rows,
+                              int vec_per_row, float4* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = n_rows * vec_per_row;
+  if (i >= total) return;
+  int64_t r = i / vec_per_row;
+  int c = (int)(i - r * vec_per_row);
+  out[i] = in[(int64_t)perm[r] * vec_per_row + c];
+}
+__global__ void k_gather_rows_scalar(const float* __restrict__ in, const int32_t* __restrict__ perm,
+                                     int64_t n_rows, int width, float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = n_rows * width;
+  if (i >= total) return;
+  int64_t r = i / width;
+  int c = (int)(i - r * width);
+  out[i] = in[(int64_t)perm[r] * width + c];
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+extern "C" int hgt_plan_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* out_bytes) {
+  HGT_REQUIRE(out_bytes, "hgt_plan_workspace_bytes: out_bytes is NULL");
+  HGT_REQUIRE(n_nodes >= 0 && n_edges >= 0 && n_nodes < 2147483000ll && n_edges < 2147483000ll,
+              "hgt_plan_workspace_bytes: n_nodes=%lld / n_edges=%lld outside the int32 index range",
+              (long long)n_nodes, (long long)n_edges);
+  PlanScratch s;
+  *out_bytes = carve(s, nullptr, n_nodes, n_edges) + 256;
+  return 0;
+}
+
+extern "C" int hgt_plan_nodes(const int64_t* node_type, int64_t n_nodes, int32_t num_types,
+                              int32_t* rank, int32_t* perm, int32_t* type_count, int32_t* sorted_flag,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(num_types >= 1 && num_types <= 4096, "hgt_plan_nodes: num_types=%d unsupported", num_types);
+  PlanScratch s;
+  size_t need = carve(s, workspace, n_nodes, 0);
+  HGT_REQUIRE(workspace_bytes >= need, "hgt_plan_nodes: workspace too small (%zu < %zu)", workspace_bytes, need);
+  HGT_CHECK_CUDA(cudaMemsetAsync(type_count, 0, sizeof(int32_t) * (num_types + 1), st));
+  int32_t one = 1;
+  HGT_CHECK_CUDA(cudaMemcpyAsync(sorted_flag, &one, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (n_nodes == 0) return 0;
+  k_node_keys<<<blocks_for(n_nodes), kThreads, sizeof(int32_t) * (num_types + 1), st>>>(
+      node_type, n_nodes, num_types, s.keys_in, s.vals_in, type_count, sorted_flag);
+  HGT_LAUNCH_CHECK();
+  size_t tmp = s.cub_bytes;
+  HGT_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, (const int32_t*)s.keys_in, s.keys_out,
+                                                 (const int32_t*)s.vals_in, perm, (int)n_nodes, 0,
+                                                 bits_for(num_types + 1), st));
+  k_inverse_perm<<<blocks_for(n_nodes), kThreads, 0, st>>>(perm, n_nodes, rank);
+  HGT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hgt_plan_edges_sort(const int64_t* edge_index, const int64_t* edge_type, const int64_t* node_type,
+                                   const int32_t* rank, int64_t n_nodes, int64_t n_edges,
+                                   int32_t num_types, int32_t num_relations, int32_t* row_ptr,
+                                   int32_t* csr_eid, int32_t* presence, int32_t* flags, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  PlanScratch s;
+  size_t need = carve(s, workspace, n_nodes, n_edges);
+  HGT_REQUIRE(workspace_bytes >= need, "hgt_plan_edges_sort: workspace too small (%zu < %zu)", workspace_bytes, need);
+  HGT_CHECK_CUDA(cudaMemsetAsync(s.counts, 0, sizeof(int32_t) * (n_nodes + 1), st));
+  HGT_CHECK_CUDA(cudaMemsetAsync(presence, 0, sizeof(int32_t) * num_types * num_relations, st));
+  HGT_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 4, st));
+  if (n_edges > 0) {
+    k_edge_keys<<<blocks_for(n_edges), kThreads, 0, st>>>(edge_index, edge_type, node_type, rank, n_nodes,
+                                                          n_edges, num_types, num_relations, s.keys_in,
+                                                          s.vals_in, s.counts, presence, flags);
+    HGT_LAUNCH_CHECK();
+  }
+  size_t tmp = s.cub_bytes;
+  HGT_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(s.cub_tmp, tmp, (const int32_t*)s.counts, row_ptr,
+                                               (int)(n_nodes + 1), st));
+  if (n_edges > 0) {
+    tmp = s.cub_bytes;
+    HGT_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, (const int32_t*)s.keys_in, s.keys_out,
+                                                   (const int32_t*)s.vals_in, csr_eid, (int)n_edges, 0,
+                                                   bits_for(n_nodes > 1 ? n_nodes : 2), st));
+  }
+  return 0;
+}
+
+extern "C" int hgt_plan_edges_fill(const int64_t* edge_index, const int64_t* edge_type, const int64_t* edge_time,
+                                   const int64_t* node_type, const int32_t* rank, const int32_t* csr_eid,
+                                   int64_t n_nodes, int64_t n_edges, int32_t num_types, int32_t num_relations,
+                                   const int32_t* pair_of, const int32_t* pair_row0, const int32_t* type_row0,
+                                   int32_t zero_row, int32_t zero_rte_row, int32_t* kv_row, int32_t* rte_row,
+                                   int32_t* flags, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_edges == 0) return 0;
+  HGT_REQUIRE((edge_time != nullptr) == (rte_row != nullptr),
+              "hgt_plan_edges_fill: edge_time and rte_row must both be given or both be NULL");
+  k_edge_fill<<<blocks_for(n_edges), kThreads, 0, st>>>(edge_index, edge_type, edge_time, node_type, rank,
+                                                        csr_eid, n_nodes, n_edges, num_types, num_relations,
+                                                        pair_of, pair_row0, type_row0, zero_row, zero_rte_row,
+                                                        kv_row, rte_row, flags);
+  HGT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges, int32_t target_edges,
+                              int32_t split_edges, int32_t* tiles, int64_t max_tiles, int32_t* d_n_tiles,
+                              int32_t* h_n_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(target_edges >= 1 && split_edges >= 1, "hgt_plan_tiles: bad tile parameters");
+  h_n_tiles[0] = h_n_tiles[1] = 0;
+  if (n_nodes == 0) return 0;
+  int tc = 2 * target_edges;
+  PlanScratch s;
+  size_t need = carve(s, workspace, n_nodes, n_edges);
+  HGT_REQUIRE(workspace_bytes >= need, "hgt_plan_tiles: workspace too small (%zu < %zu)", workspace_bytes, need);
+  int64_t* packed = s.packed;
+  void* tmp = s.cub_tmp;
+  size_t tmp_bytes = s.cub_bytes;
+  k_tile_emit_counts<<<blocks_for(n_nodes + 1), kThreads, 0, st>>>(row_ptr, n_nodes, tc, split_edges, packed);
+  HGT_LAUNCH_CHECK();
+  HGT_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int64_t*)packed, packed,
+                                               (int)(n_nodes + 1), st));
+  k_tile_write<<<blocks_for(n_nodes + 1), kThreads, 0, st>>>(row_ptr, n_nodes, tc, split_edges, packed, tiles,
+                                                             max_tiles, d_n_tiles);
+  HGT_LAUNCH_CHECK();
+  HGT_CHECK_CUDA(cudaMemcpyAsync(h_n_tiles, d_n_tiles, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  HGT_CHECK_CUDA(cudaStreamSynchronize(st));
+  HGT_REQUIRE(h_n_tiles[0] <= max_tiles, "hgt_plan_tiles: %d tiles exceed max_tiles=%lld", h_n_tiles[0],
+              (long long)max_tiles);
+  if (h_n_tiles[0] > 0) {
+    k_tile_close<<<blocks_for(h_n_tiles[0]), kThreads, 0, st>>>(row_ptr, n_nodes, tiles, d_n_tiles);
+    HGT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_rows, int32_t width, float* out,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_rows == 0) return 0;
+  if (width % 4 == 0 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+    k_gather_rows<<<blocks_for(n_rows * (width / 4)), kThreads, 0, st>>>((const float4*)in, perm, n_rows,
+                                                                         width / 4, (float4*)out);
+  } else {
+    k_gather_rows_scalar<<<blocks_for(n_rows * width), kThreads, 0, st>>>(in, perm, n_rows, width, out);
+  }
+  HGT_LAUNCH_CHECK();
+  return 0;
+}

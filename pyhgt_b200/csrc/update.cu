@@ -1,0 +1,87 @@
+// HGTConv.update epilogue (conv.py:129-133): sigmoid(skip)-gated residual + per-type LayerNorm.
+// One warp per node row; the row (d <= 1024 floats) stays in registers between the two LayerNorm passes.
+// HBM-bound: reads o and x (2*d*4 B), writes out (d*4 B) per node.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxPerLane = 32;   // d <= 1024
+
+__global__ void __launch_bounds__(256)
+k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
+                  int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
+                  const float* __restrict__ norm_b, const int32_t* __restrict__ perm, int64_t n_nodes, int d,
+                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  // node type of this rank: types are contiguous in rank order, T is small
+  int t = 0;
+  while (t < T && row >= type_row0[t + 1]) ++t;
+  float* orow = out + (perm ? (int64_t)perm[row] : row) * d;
+  if (t >= T) {                                  // type outside [0,T): the reference leaves zeros (conv.py:120)
+    for (int c = lane; c < d; c += 32) orow[c] = 0.f;
+    return;
+  }
+  const float alpha = 1.0f / (1.0f + __expf(-skip[t]));    // torch.sigmoid(self.skip[t]), conv.py:129
+  const float* op = o + row * d;
+  const float* xp = x + row * d;
+  float y[kMaxPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    int c = lane + i * 32;
+    if (c < d) {
+      y[i] = op[c] * alpha + xp[c] * (1.0f - alpha);       // conv.py:131,133
+      sum += y[i];
+    } else {
+      y[i] = 0.f;
+    }
+  }
+  if (norm_w == nullptr) {
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      int c = lane + i * 32;
+      if (c < d) orow[c] = y[i];
+    }
+    return;
+  }
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float mean = sum / d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    int c = lane + i * 32;
+    if (c < d) {
+      float dlt = y[i] - mean;
+      var = fmaf(dlt, dlt, var);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+  const float rstd = rsqrtf(var / d + 1e-5f);              // nn.LayerNorm eps (conv.py:40)
+  const float* w = norm_w + (int64_t)t * d;
+  const float* b = norm_b + (int64_t)t * d;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    int c = lane + i * 32;
+    if (c < d) orow[c] = (y[i] - mean) * rstd * w[c] + b[c];
+  }
+}
+
+}  // namespace
+
+extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
+                                   const float* skip, const float* norm_w, const float* norm_b,
+                                   const int32_t* perm, int64_t n_nodes, int32_t d, float* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(d >= 1 && d <= 32 * kMaxPerLane, "hgt_update_epilogue: d=%d unsupported (max %d)", d,
+              32 * kMaxPerLane);
+  HGT_REQUIRE((norm_w == nullptr) == (norm_b == nullptr), "hgt_update_epilogue: norm_w/norm_b must go together");
+  if (n_nodes == 0) return 0;
+  const int warps_per_block = 8;
+  unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
+  k_update_epilogue<<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, num_types, skip, norm_w, norm_b,
+                                                           perm, n_nodes, d, out);
+  HGT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,247 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  The CUDA path (through the C ABI) is compared
+with (a) golden outputs of the reference itself (tests/golden, made by oracle/make_golden.py) and (b) the CPU
+oracle on seeded graphs.  Tolerance from BASELINE.json north_star: 1e-3 (allclose rtol=atol=1e-3 and relative
+Frobenius error <= 1e-3); index handling is bit-exact."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import hgt_oracle          # noqa: E402
+from pyhgt_b200 import synth           # noqa: E402
+from tests.conftest import load_golden, CONV_FIXTURES  # noqa: E402
+
+RTOL = ATOL = 1e-3
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _close(a, b, what, atol=ATOL):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    fro = ((a - b).norm() / b.norm().clamp_min(1e-30)).item() if a.numel() else 0.0
+    assert torch.allclose(a, b, rtol=RTOL, atol=atol), "%s: max abs err %.3g (rel fro %.3g)" % (what, err, fro)
+    assert fro <= 1e-3, "%s: relative Frobenius error %.3g" % (what, fro)
+
+
+def _module_from_fixture(fx, dev):
+    import pyhgt_b200
+    c = fx["cfg"]
+    m = pyhgt_b200.HGTConv(c["in_dim"], c["out_dim"], c["num_types"], c["num_relations"], c["n_heads"], 0.2,
+                           c["use_norm"], c["use_RTE"])
+    m.load_state_dict(fx["state_dict"])
+    return m.to(dev).eval()
+
+
+def _run(m, fx, dev, key="node_inp"):
+    with torch.no_grad():
+        out = m(fx[key].to(dev), fx["node_type"].to(dev), fx["edge_index"].to(dev), fx["edge_type"].to(dev),
+                fx["edge_time"].to(dev))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", CONV_FIXTURES)
+def test_forward_matches_reference_golden(name, variant):
+    dev = _dev()
+    fx = load_golden(name)
+    m = _module_from_fixture(fx, dev)
+    m.edge_variant = variant
+    out = _run(m, fx, dev)
+    _close(out, fx["out"], "%s out (variant %d)" % (name, variant))
+    _close(m.att, fx["att"], "%s att (variant %d)" % (name, variant), atol=1e-4)
+
+
+def test_four_argument_forward_without_rte():
+    dev = _dev()
+    fx = load_golden("c1_norte")
+    m = _module_from_fixture(fx, dev)
+    with torch.no_grad():
+        out = m(fx["node_inp"].to(dev), fx["node_type"].to(dev), fx["edge_index"].to(dev), fx["edge_type"].to(dev))
+    _close(out, fx["out"], "4-arg forward")
+
+
+def test_plan_is_bit_exact():
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    g = synth.make_random(5000, 40000, 5, 7, seed=3, isolated_frac=0.2, self_loops=100, duplicate_edges=500)
+    nt, ei, et, tm = g.node_type, g.edge_index, g.edge_type, g.edge_time
+    plan = P.build_plan(nt.to(dev), ei.to(dev), et.to(dev), tm.to(dev), g.num_types, g.num_relations)
+    perm = torch.argsort(nt, stable=True)
+    assert torch.equal(plan.perm.cpu().long(), perm)
+    rank = torch.empty_like(perm); rank[perm] = torch.arange(perm.numel())
+    assert torch.equal(plan.rank.cpu().long(), rank)
+    dst_rank = rank[ei[1]]
+    order = torch.argsort(dst_rank, stable=True)
+    assert torch.equal(plan.csr_eid.cpu().long(), order)
+    counts = torch.bincount(dst_rank, minlength=g.num_nodes)
+    row_ptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    assert torch.equal(plan.row_ptr.cpu().long(), row_ptr)
+    # gather rows: pair (src_type, rel) -> base + rank-in-type
+    type_count = torch.bincount(nt, minlength=g.num_types)
+    type_row0 = torch.cat([torch.zeros(1, dtype=torch.long), type_count.cumsum(0)])
+    pair_id = {p: i for i, p in enumerate(plan.pairs)}
+    src_t = nt[ei[0]]
+    exp_pairs = sorted(set(zip(src_t.tolist(), et.tolist())))
+    assert plan.pairs == exp_pairs
+    e_sorted = order
+    exp_row = torch.tensor([plan.pair_row0[pair_id[(int(src_t[e]), int(et[e]))]] +
+                            int(rank[ei[0, e]] - type_row0[src_t[e]]) for e in e_sorted.tolist()])
+    assert torch.equal(plan.kv_row.cpu().long(), exp_row)
+    exp_rte = torch.tensor([pair_id[(int(src_t[e]), int(et[e]))] * 240 + int(tm[e]) for e in e_sorted.tolist()])
+    assert torch.equal(plan.rte_row.cpu().long(), exp_rte)
+    # tiles cover every destination and every edge exactly once, in order
+    tiles = plan.tiles.cpu()[:plan.n_tiles].tolist()
+    d, e = 0, 0
+    for t in tiles:
+        if t[1] >= 0:
+            assert t[0] == d and t[2] == e and t[3] == int(row_ptr[t[1]])
+            d, e = t[1], t[3]
+        else:
+            assert t[0] == d or t[0] == d - 1
+            assert t[2] == e
+            e = t[3]
+            d = t[0] + 1
+    assert d == g.num_nodes and e == g.num_edges
+
+
+def test_invalid_indices_raise():
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    g = synth.make_c1()
+    bad = g.edge_index.clone(); bad[0, 5] = g.num_nodes
+    with pytest.raises(IndexError):
+        P.build_plan(g.node_type.to(dev), bad.to(dev), g.edge_type.to(dev), None, 2, 1)
+    tm = g.edge_time.clone(); tm[3] = 240
+    with pytest.raises(IndexError):
+        P.build_plan(g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev), tm.to(dev), 2, 1)
+    with pytest.raises(ValueError):
+        P.build_plan(g.node_type.to(dev), g.edge_index.to(dev).int(), g.edge_type.to(dev), None, 2, 1)
+
+
+def test_out_of_range_relation_and_type_follow_reference_semantics():
+    """Edges whose relation (or endpoint type) matches no <s,t,r> triple keep score 0 / message 0 but still
+    take part in the destination's softmax (conv.py:68-69,108); nodes of unknown type get zero rows (conv.py:120)."""
+    import pyhgt_b200
+    dev = _dev()
+    g = synth.make_random(300, 3000, 3, 4, seed=9)
+    g.edge_type[::7] = 9           # relation outside [0,R)
+    g.node_type[::11] = 5          # type outside [0,T)
+    torch.manual_seed(1)
+    m = pyhgt_b200.HGTConv(32, 32, 3, 4, 4, 0.2, True, True).eval()
+    x = torch.randn(300, 32)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref, ref_att = hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index, g.edge_type, g.edge_time,
+                                                   num_types=3, num_relations=4, n_heads=4)
+    m = m.to(dev)
+    with torch.no_grad():
+        out = m(x.to(dev), g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev), g.edge_time.to(dev))
+    _close(out, ref, "out with unmatched edges")
+    _close(m.att, ref_att, "att with unmatched edges", atol=1e-4)
+
+
+def test_typed_linear_simt_matches_torch():
+    import numpy as np
+    from pyhgt_b200 import _lib, plan as P
+    dev = _dev()
+    torch.manual_seed(0)
+    K, width = 100, 36
+    a = torch.randn(777, K, device=dev)
+    w = torch.randn(3 * width, K, device=dev)
+    b = torch.randn(3 * width, device=dev)
+    out = torch.zeros(777 * width + 500 * 2 * width, device=dev)
+    # group 0: rows 0..499 -> two blocks interleaved [500, 2*width] at offset 777*width ; group 1: rows 500..776 -> block 0
+    groups = [(0, 500, width, 2, 0, 1), (500, 277, 0, 1, 2, 0)]
+    cblocks = [(777 * width, 2 * width), (777 * width + width, 2 * width), (500 * width, width)]
+    g_dev, g_host, n_g, c_dev = P._pack_groups(groups, cblocks, dev)
+    _lib.call("hgt_typed_linear", a.data_ptr(), K, w.data_ptr(), b.data_ptr(), K, width, g_dev.data_ptr(),
+              g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), 1, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref0 = a[:500].double() @ w[width:].double().t() + b[width:].double()
+    got0 = out[777 * width:].view(500, 2 * width)
+    assert torch.allclose(got0.double(), ref0, rtol=1e-5, atol=1e-4)
+    ref1 = a[500:].double() @ w[:width].double().t()
+    got1 = out[500 * width:777 * width].view(277, width)
+    assert torch.allclose(got1.double(), ref1, rtol=1e-5, atol=1e-4)
+
+
+def test_edge_order_permutation_invariance():
+    """Permuting the edge list permutes att rows and leaves out unchanged (to fp tolerance)."""
+    dev = _dev()
+    fx = load_golden("rand_t3r4_dk4")
+    m = _module_from_fixture(fx, dev)
+    out = _run(m, fx, dev)
+    att = m.att.clone()
+    perm = torch.randperm(fx["edge_type"].numel(), generator=torch.Generator().manual_seed(0))
+    fx2 = dict(fx)
+    fx2["edge_index"] = fx["edge_index"][:, perm]
+    fx2["edge_type"] = fx["edge_type"][perm]
+    fx2["edge_time"] = fx["edge_time"][perm]
+    out2 = _run(m, fx2, dev)
+    _close(out2, out, "out under edge permutation", atol=1e-5)
+    _close(m.att, att[perm.to(dev)], "att under edge permutation", atol=1e-6)
+
+
+def test_empty_edge_list_gives_bias_path():
+    import pyhgt_b200
+    dev = _dev()
+    torch.manual_seed(0)
+    m = pyhgt_b200.HGTConv(32, 32, 2, 2, 4, 0.2, True, False).to(dev).eval()
+    x = torch.randn(50, 32, device=dev)
+    nt = torch.randint(0, 2, (50,), device=dev)
+    with torch.no_grad():
+        out = m(x, nt, torch.zeros(2, 0, dtype=torch.long, device=dev), torch.zeros(0, dtype=torch.long, device=dev))
+    # agg = 0 -> gelu(0) = 0 -> a_linear gives its bias
+    ref = torch.empty_like(out)
+    for t in range(2):
+        sel = nt == t
+        a = torch.sigmoid(m.skip[t])
+        y = m.a_linears[t].bias * a + x[sel] * (1 - a)
+        ref[sel] = torch.nn.functional.layer_norm(y, (32,), m.norms[t].weight, m.norms[t].bias, 1e-5)
+    _close(out, ref, "empty edge list")
+    assert m.att.shape == (0, 4)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_mag_shaped_medium_graph_vs_oracle(variant):
+    """ogbn-mag-shaped graph at 0.5 % scale (~105k edges, d=256, H=8): CUDA vs CPU oracle."""
+    import pyhgt_b200
+    dev = _dev()
+    g = synth.make_mag_shaped(scale=0.005, seed=7)
+    torch.manual_seed(3)
+    m = pyhgt_b200.HGTConv(256, 256, 4, 4, 8, 0.2, True, False).eval()
+    x = torch.randn(g.num_nodes, 256)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref, ref_att = hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index, g.edge_type, None,
+                                                   num_types=4, num_relations=4, n_heads=8, use_RTE=False)
+    m = m.to(dev)
+    m.edge_variant = variant
+    with torch.no_grad():
+        out = m(x.to(dev), g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev))
+    _close(out, ref, "mag x0.005 out")
+    _close(m.att, ref_att, "mag x0.005 att", atol=1e-4)
+
+
+def test_hub_split_matches_unsplit(monkeypatch):
+    """Force hub splitting at a tiny threshold: result must not change."""
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    fx = load_golden("hub_h2")
+    m = _module_from_fixture(fx, dev)
+    out_ref = _run(m, fx, dev)
+    att_ref = m.att.clone()
+    monkeypatch.setattr(P, "TILE_SPLIT_EDGES", 37)
+    monkeypatch.setattr(P, "TILE_TARGET_EDGES", 8)
+    P.clear_plan_cache()
+    for variant in (1, 2):
+        m.edge_variant = variant
+        fx2 = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in fx.items()}
+        out = _run(m, fx2, dev)
+        _close(out, out_ref, "hub split out (variant %d)" % variant, atol=1e-5)
+        _close(m.att, att_ref, "hub split att", atol=1e-6)
+        _close(out, fx["out"], "hub split vs golden")
+    P.clear_plan_cache()
