@@ -135,12 +135,16 @@ int hgt_concat_linears(const float* const* w, const float* const* b, int32_t num
 
 /* out[cblock c of group g][m, n] = sum_k A[a_row0_g + m, k] * W[w_row0_g + c*cb_width + n, k] (+ bias).
  * fp32 in / fp32 out.  `impl`: 0 = auto, 1 = SIMT fp32 FMA kernel, 2 = tcgen05 split-bf16 tensor-core
- * kernel (fp32-accurate to ~2^-16).  groups/cblocks are DEVICE arrays; h_groups is the same table on
- * the host (used to size the grid; no device read-back). */
+ * kernel (three bf16 products of a hi/lo operand split accumulated in one fp32 TMEM accumulator: accurate
+ * to ~1e-5 relative; needs cb_width % 16 == 0 and K >= 64, workspace for the split operands).
+ * groups/cblocks are DEVICE arrays; h_groups is the same table on the host (used to size the grid; no
+ * device read-back). */
+int hgt_typed_linear_workspace_bytes(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K,
+                                     int32_t cb_width, int32_t impl, size_t* out_bytes);
 int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* bias, int32_t K,
                      int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
                      int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, int32_t impl,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused edge kernel: gather -> relation-specific score -> softmax by destination -> weighted sum

@@ -128,6 +128,15 @@ class HGTConv(nn.Module):
             tab = self._ptr_tables[name] = _PointerTable()
         return tab.get(tensors, device)
 
+    def _typed_linear(self, a, lda, w, bias, k, width, table, out, impl, st):
+        """hgt_typed_linear with its (impl-dependent) workspace; table = (groups_dev, groups_host, n, cblocks_dev)."""
+        g_dev, g_host, n_g, c_dev = table
+        ws_bytes = ctypes.c_size_t()
+        _lib.call("hgt_typed_linear_workspace_bytes", g_host.ctypes.data, n_g, k, width, impl, ctypes.byref(ws_bytes))
+        ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=out.device)
+        _lib.call("hgt_typed_linear", a.data_ptr(), lda, w.data_ptr(), _lib.ptr(bias), k, width, g_dev.data_ptr(),
+                  g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), impl, ws.data_ptr(), ws.numel(), st)
+
     def _check_inputs(self, node_inp, edge_time):
         if node_inp.device.type != "cuda":
             raise _lib.HgtError("pyhgt_b200.HGTConv runs on CUDA tensors only (got %s): there is no CPU "
@@ -193,22 +202,16 @@ class HGTConv(nn.Module):
         q_tab = proj[lt.q_off:lt.q_off + N * d]
         kv_tab = proj[lt.kv_off:]
         kv_tab[plan.kv_rows * 2 * d:].zero_()
-        g_dev, g_host, n_g, c_dev = lt.proj_groups
-        _lib.call("hgt_typed_linear", x_sorted.data_ptr(), d_in, w_cat.data_ptr(), b_cat.data_ptr(), d_in, d,
-                  g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(), proj.data_ptr(), self.linear_impl, st)
+        self._typed_linear(x_sorted, d_in, w_cat, b_cat, d_in, d, lt.proj_groups, proj, self.linear_impl, st)
         kvr = None
         if self.use_RTE:
             # RT = lin(emb.weight) [240,d] (conv.py:299), then projected with every pair's K'/V' weights (no bias)
             rt = torch.empty((_plan.RTE_MAX_LEN, d_in), **f32)
-            one_g = lt.rt_group
-            _lib.call("hgt_typed_linear", self.emb.emb.weight.data_ptr(), d_in, self.emb.lin.weight.data_ptr(),
-                      self.emb.lin.bias.data_ptr(), d_in, d_in, one_g[0].data_ptr(), one_g[1].ctypes.data, 1,
-                      one_g[3].data_ptr(), rt.data_ptr(), 1, st)
+            self._typed_linear(self.emb.emb.weight, d_in, self.emb.lin.weight, self.emb.lin.bias, d_in, d_in,
+                               lt.rt_group, rt, 1, st)
             kvr = torch.empty((P * _plan.RTE_MAX_LEN + 1) * 2 * d, **f32)
             kvr[P * _plan.RTE_MAX_LEN * 2 * d:].zero_()
-            g2, g2h, n_g2, c2 = lt.rte_groups
-            _lib.call("hgt_typed_linear", rt.data_ptr(), d_in, w_cat.data_ptr(), None, d_in, d, g2.data_ptr(),
-                      g2h.ctypes.data, n_g2, c2.data_ptr(), kvr.data_ptr(), 1, st)
+            self._typed_linear(rt, d_in, w_cat, None, d_in, d, lt.rte_groups, kvr, 1, st)
 
         # 3. fused edge kernel -> gelu(aggregate)
         ws_bytes = ctypes.c_size_t()
@@ -234,9 +237,7 @@ class HGTConv(nn.Module):
         ba = self._ptrs("ba", [l.bias for l in self.a_linears], dev)
         _lib.call("hgt_concat_linears", wa.data_ptr(), ba.data_ptr(), T, d, d, wa_cat.data_ptr(), ba_cat.data_ptr(), st)
         o = torch.empty((N, d), **f32)
-        g3, g3h, n_g3, c3 = lt.upd_groups
-        _lib.call("hgt_typed_linear", g_act.data_ptr(), d, wa_cat.data_ptr(), ba_cat.data_ptr(), d, d, g3.data_ptr(),
-                  g3h.ctypes.data, n_g3, c3.data_ptr(), o.data_ptr(), self.linear_impl, st)
+        self._typed_linear(g_act, d, wa_cat, ba_cat, d, d, lt.upd_groups, o, self.linear_impl, st)
         if self.training and self.drop.p > 0:
             o = self.drop(o)                                       # conv.py:125 (train mode only)
         norm_w = norm_b = None

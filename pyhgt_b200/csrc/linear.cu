@@ -6,8 +6,10 @@
 
 int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float* bias, int32_t K,
                         int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
-                        int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, cudaStream_t st);
+                        int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st);
 bool hgt_typed_linear_tc_supported(int64_t lda, int32_t K, int32_t cb_width);
+size_t hgt_typed_linear_tc_workspace(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K, int32_t cb_width);
 
 namespace {
 
@@ -201,10 +203,18 @@ extern "C" int hgt_concat_linears(const float* const* w, const float* const* b, 
   return 0;
 }
 
+extern "C" int hgt_typed_linear_workspace_bytes(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K,
+                                                int32_t cb_width, int32_t impl, size_t* out_bytes) {
+  HGT_REQUIRE(out_bytes && (h_groups || n_groups == 0), "hgt_typed_linear_workspace_bytes: NULL argument");
+  if (impl == 0) impl = hgt_typed_linear_tc_supported(K, K, cb_width) ? 2 : 1;
+  *out_bytes = (impl == 2 && n_groups > 0) ? hgt_typed_linear_tc_workspace(h_groups, n_groups, K, cb_width) : 0;
+  return 0;
+}
+
 extern "C" int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* bias, int32_t K,
                                 int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
                                 int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, int32_t impl,
-                                void* stream_) {
+                                void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(n_groups >= 0 && n_groups <= kMaxGroups, "hgt_typed_linear: n_groups=%d exceeds %d", n_groups,
               kMaxGroups);
@@ -215,7 +225,8 @@ extern "C" int hgt_typed_linear(const float* A, int64_t lda, const float* W, con
     HGT_REQUIRE(hgt_typed_linear_tc_supported(lda, K, cb_width),
                 "hgt_typed_linear: tensor-core kernel does not support lda=%lld K=%d cb_width=%d",
                 (long long)lda, K, cb_width);
-    return hgt_typed_linear_tc(A, lda, W, bias, K, cb_width, groups, h_groups, n_groups, cblocks, out, st);
+    return hgt_typed_linear_tc(A, lda, W, bias, K, cb_width, groups, h_groups, n_groups, cblocks, out, workspace,
+                               workspace_bytes, st);
   }
   HGT_REQUIRE(impl == 1, "hgt_typed_linear: unknown impl %d", impl);
   TilePrefix tp;

@@ -1,15 +1,390 @@
-// tcgen05 (5th-gen tensor core) grouped GEMM for the typed linears — placeholder until the
-// split-bf16 kernel lands; hgt_typed_linear falls back to the fp32 SIMT kernel.
+// Typed linear layers on the 5th-generation tensor cores (tcgen05) with fp32-grade accuracy.
+//
+// fp32 operands are split into two bf16 terms, x = x_hi + x_lo (|x - x_hi - x_lo| <= 2^-17 |x|), and
+//     A*W^T  ~=  A_hi*W_hi^T + A_hi*W_lo^T + A_lo*W_hi^T            (dropped term ~2^-18)
+// is accumulated in ONE fp32 TMEM accumulator by running three bf16 passes over K inside the same
+// tile: 3 tensor-core products at the bf16 rate instead of an fp32 FMA GEMM, error ~1e-5 relative —
+// far inside the 1e-3 parity bar, where a single bf16 or tf32 product would not be.
+//
+// Kernel (one CTA per 128 x BN output tile, 2 CTAs per SM so one CTA's epilogue overlaps the other's
+// main loop):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) into a STAGES-deep smem ring
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16/bf16)
+//   warps 2-5: epilogue      — tcgen05.ld 32x32b -> +bias -> st.global into the (strided) column block
+// Output tiles follow the same group / column-block tables as the SIMT kernel in linear.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-bool hgt_typed_linear_tc_supported(int64_t lda, int32_t K, int32_t cb_width) {
-  (void)lda; (void)K; (void)cb_width;
-  return false;
+namespace {
+
+constexpr int kMaxGroups = 64;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;              // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_THREADS = 192;
+constexpr int UMMA_K = 16;
+
+struct TcTilePrefix {
+  int32_t first_tile[kMaxGroups + 1];
+  int32_t n_tiles_n;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 
-int hgt_typed_linear_tc(const float*, int64_t, const float*, const float*, int32_t, int32_t,
-                        const hgt_lin_group*, const hgt_lin_group*, int32_t, const hgt_lin_cblock*, float*,
-                        cudaStream_t) {
-  hgt_set_error("hgt_typed_linear: tensor-core kernel not built");
-  return 1;
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA format): rows of 128 bytes,
+// 8-row swizzle atoms 1024 bytes apart (SBO), version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+// ---- fp32 -> (bf16 hi, bf16 lo) split ------------------------------------------------------------
+__global__ void k_split_bf16(const float* __restrict__ in, int64_t ld_in, int64_t rows, int K, int Kp,
+                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int vec_per_row = Kp / 4;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows * vec_per_row) return;
+  int64_t r = i / vec_per_row;
+  int c = (int)(i - r * vec_per_row) * 4;
+  float v[4];
+  const float* src = in + r * ld_in + c;
+  if (c + 3 < K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    float4 t = *reinterpret_cast<const float4*>(src);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (c + j < K) ? src[j] : 0.f;
+  }
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(v[j]);
+    l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+  }
+  *reinterpret_cast<uint2*>(hi + r * Kp + c) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + r * Kp + c) = *reinterpret_cast<uint2*>(l);
+}
+
+// ---- the GEMM -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_typed_linear_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const float* __restrict__ bias, int Kp, int cb_width, int BN, int stages, int tmem_cols,
+                  const hgt_lin_group* __restrict__ groups, int n_groups,
+                  const hgt_lin_cblock* __restrict__ cblocks, float* __restrict__ out, TcTilePrefix tp) {
+  extern __shared__ unsigned char smem_dyn[];
+  // carve: [stages][A 16 KB | B BN*128 B] (1024-aligned), then barriers, tmem pointer, bias tile
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;
+  const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t b_bytes_al = (b_bytes + 1023) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + stages;
+  uint64_t* tmem_full_bar = bars + 2 * stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile decode ----
+  int tile = blockIdx.x;
+  int g = 0;
+  while (g + 1 < n_groups && tile >= tp.first_tile[g + 1]) ++g;
+  const hgt_lin_group grp = groups[g];
+  int local = tile - tp.first_tile[g];
+  const int per_m = grp.n_cblocks * tp.n_tiles_n;
+  const int mt = local / per_m;
+  local -= mt * per_m;
+  const int cb = local / tp.n_tiles_n;
+  const int nt = local - cb * tp.n_tiles_n;
+  const hgt_lin_cblock cblk = cblocks[grp.cb_first + cb];
+  const int64_t m0 = (int64_t)mt * TC_BM;
+  const int n0 = nt * BN;
+  const int a_row = (int)(grp.a_row0 + m0);
+  const int w_row = grp.w_row0 + cb * cb_width + n0;
+  const int rows_here = (int)min((int64_t)TC_BM, grp.m - m0);
+  const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
+  const int total_iters = 3 * k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(s_u32(&full_bar[s]), 1);
+      mbar_init(s_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(s_u32(tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int c = threadIdx.x - 64; c < BN; c += TC_THREADS - 64)
+      s_bias[c] = (grp.has_bias && bias) ? bias[w_row + c] : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(s_u32(&empty_bar[s]), ph ^ 1u);
+        const int pass = it / k_blocks;                    // 0: hi*hi, 1: hi*lo, 2: lo*hi
+        const int kb = it - pass * k_blocks;
+        const CUtensorMap* ma = (pass == 2) ? &map_a_lo : &map_a_hi;
+        const CUtensorMap* mw = (pass == 1) ? &map_w_lo : &map_w_hi;
+        const uint32_t bar = s_u32(&full_bar[s]);
+        const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+        mbar_expect_tx(bar, a_bytes + b_bytes);
+        tma_load_2d(sa, ma, kb * TC_BK, a_row, bar);
+        tma_load_2d(sa + a_bytes, mw, kb * TC_BK, w_row, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
+      // N>>3 at bits 17-22, M>>4 at bits 24-28
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(s_u32(&full_bar[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t da = make_sw128_desc(sa);
+        const uint64_t db = make_sw128_desc(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_bf16_ss(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(s_u32(&empty_bar[s]));                  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(s_u32(tmem_full_bar));                    // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    mbar_wait(s_u32(tmem_full_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* orow = out + cblk.out_off + (m0 + row) * cblk.ld + n0;
+    const bool row_ok = row < rows_here;
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j + 0]) + s_bias[c + j + 0];
+          v.y = __uint_as_float(r[j + 1]) + s_bias[c + j + 1];
+          v.z = __uint_as_float(r[j + 2]) + s_bias[c + j + 2];
+          v.w = __uint_as_float(r[j + 3]) + s_bias[c + j + 3];
+          *reinterpret_cast<float4*>(orow + c + j) = v;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int Kp, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  HGT_REQUIRE(fn != nullptr, "hgt_typed_linear: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HGT_REQUIRE(r == CUDA_SUCCESS, "hgt_typed_linear: cuTensorMapEncodeTiled failed (%d) rows=%lld Kp=%d box=%d",
+              (int)r, (long long)rows, Kp, box_rows);
+  return 0;
+}
+
+int pick_bn(int cb_width) {
+  for (int bn = 128; bn >= 16; bn -= 16)
+    if (cb_width % bn == 0) return bn;
+  return 0;
+}
+
+void extents(const hgt_lin_group* h_groups, int n_groups, int cb_width, int64_t* a_rows, int64_t* w_rows) {
+  *a_rows = 0;
+  *w_rows = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    int64_t a = h_groups[g].a_row0 + h_groups[g].m;
+    int64_t w = (int64_t)h_groups[g].w_row0 + (int64_t)h_groups[g].n_cblocks * cb_width;
+    if (a > *a_rows) *a_rows = a;
+    if (w > *w_rows) *w_rows = w;
+  }
+}
+
+}  // namespace
+
+bool hgt_typed_linear_tc_supported(int64_t lda, int32_t K, int32_t cb_width) {
+  (void)lda;
+  return cb_width % 16 == 0 && pick_bn(cb_width) > 0 && K >= TC_BK;
+}
+
+size_t hgt_typed_linear_tc_workspace(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K, int32_t cb_width) {
+  int64_t a_rows, w_rows;
+  extents(h_groups, n_groups, cb_width, &a_rows, &w_rows);
+  const int Kp = (K + 7) / 8 * 8;
+  return 4 * 256 + 2 * hgt_align_up((size_t)a_rows * Kp * 2, 256) + 2 * hgt_align_up((size_t)w_rows * Kp * 2, 256);
+}
+
+int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float* bias, int32_t K, int32_t cb_width,
+                        const hgt_lin_group* groups, const hgt_lin_group* h_groups, int32_t n_groups,
+                        const hgt_lin_cblock* cblocks, float* out, void* workspace, size_t workspace_bytes,
+                        cudaStream_t st) {
+  const int BN = pick_bn(cb_width);
+  HGT_REQUIRE(BN > 0, "hgt_typed_linear(tc): cb_width=%d has no multiple-of-16 tile", cb_width);
+  const int Kp = (K + 7) / 8 * 8;
+  int64_t a_rows, w_rows;
+  extents(h_groups, n_groups, cb_width, &a_rows, &w_rows);
+  size_t need = hgt_typed_linear_tc_workspace(h_groups, n_groups, K, cb_width);
+  HGT_REQUIRE(workspace && workspace_bytes >= need, "hgt_typed_linear(tc): workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  char* p = reinterpret_cast<char*>(hgt_align_up(reinterpret_cast<size_t>(workspace), 256));
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(p); p += hgt_align_up((size_t)a_rows * Kp * 2, 256);
+  __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(p); p += hgt_align_up((size_t)a_rows * Kp * 2, 256);
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(p); p += hgt_align_up((size_t)w_rows * Kp * 2, 256);
+  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(p);
+  {
+    int64_t n = a_rows * (Kp / 4);
+    if (n > 0) k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, lda, a_rows, K, Kp, a_hi, a_lo);
+    HGT_LAUNCH_CHECK();
+    n = w_rows * (Kp / 4);
+    if (n > 0) k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, K, w_rows, K, Kp, w_hi, w_lo);
+    HGT_LAUNCH_CHECK();
+  }
+  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
+  int rc;
+  if ((rc = make_map(&m_a_hi, a_hi, a_rows, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&m_a_lo, a_lo, a_rows, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&m_w_hi, w_hi, w_rows, Kp, BN))) return rc;
+  if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, BN))) return rc;
+
+  TcTilePrefix tp;
+  tp.n_tiles_n = cb_width / BN;
+  int64_t total = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    tp.first_tile[g] = (int32_t)total;
+    total += (h_groups[g].m + TC_BM - 1) / TC_BM * h_groups[g].n_cblocks * tp.n_tiles_n;
+    HGT_REQUIRE(total < 2147483647ll, "hgt_typed_linear(tc): too many tiles");
+  }
+  tp.first_tile[n_groups] = (int32_t)total;
+  if (total == 0) return 0;
+
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;
+  const uint32_t b_bytes_al = ((uint32_t)BN * TC_BK * 2 + 1023) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  int stages = (int)((100 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  int tmem_cols = 32;
+  while (tmem_cols < BN) tmem_cols <<= 1;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4 + 64;
+  HGT_CHECK_CUDA(cudaFuncSetAttribute(k_typed_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_typed_linear_tc<<<(unsigned)total, TC_THREADS, smem, st>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, bias, Kp, cb_width,
+                                                               BN, stages, tmem_cols, groups, n_groups, cblocks, out,
+                                                               tp);
+  HGT_LAUNCH_CHECK();
+  return 0;
 }

@@ -159,7 +159,8 @@ def test_typed_linear_simt_matches_torch():
     cblocks = [(777 * width, 2 * width), (777 * width + width, 2 * width), (500 * width, width)]
     g_dev, g_host, n_g, c_dev = P._pack_groups(groups, cblocks, dev)
     _lib.call("hgt_typed_linear", a.data_ptr(), K, w.data_ptr(), b.data_ptr(), K, width, g_dev.data_ptr(),
-              g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), 1, torch.cuda.current_stream().cuda_stream)
+              g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), 1, None, 0,
+              torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref0 = a[:500].double() @ w[width:].double().t() + b[width:].double()
     got0 = out[777 * width:].view(500, 2 * width)
@@ -245,3 +246,34 @@ def test_hub_split_matches_unsplit(monkeypatch):
         _close(m.att, att_ref, "hub split att", atol=1e-6)
         _close(out, fx["out"], "hub split vs golden")
     P.clear_plan_cache()
+
+
+@pytest.mark.parametrize("K,width,m_rows", [(256, 256, 1000), (64, 64, 130), (400, 400, 300), (128, 48, 257), (104, 32, 64)])
+def test_typed_linear_tensor_core_matches_fp64(K, width, m_rows):
+    """tcgen05 split-bf16 GEMM (impl 2) against float64: error must be ~1e-5 relative, far inside 1e-3."""
+    import ctypes
+    from pyhgt_b200 import _lib, plan as P
+    dev = _dev()
+    torch.manual_seed(K + width)
+    a = torch.randn(m_rows + 77, K, device=dev)
+    w = torch.randn(3 * width, K, device=dev) / K ** 0.5
+    b = torch.randn(3 * width, device=dev)
+    out = torch.full((m_rows * width + 77 * 2 * width,), float("nan"), device=dev)
+    groups = [(0, m_rows, 0, 1, 0, 1), (m_rows, 77, width, 2, 1, 0)]
+    cblocks = [(0, width), (m_rows * width, 2 * width), (m_rows * width + width, 2 * width)]
+    g_dev, g_host, n_g, c_dev = P._pack_groups(groups, cblocks, dev)
+    ws_bytes = ctypes.c_size_t()
+    _lib.call("hgt_typed_linear_workspace_bytes", g_host.ctypes.data, n_g, K, width, 2, ctypes.byref(ws_bytes))
+    ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=dev)
+    _lib.call("hgt_typed_linear", a.data_ptr(), K, w.data_ptr(), b.data_ptr(), K, width, g_dev.data_ptr(),
+              g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), 2, ws.data_ptr(), ws.numel(),
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref0 = a[:m_rows].double() @ w[:width].double().t() + b[:width].double()
+    got0 = out[:m_rows * width].view(m_rows, width).double()
+    ref1 = a[m_rows:].double() @ w[width:].double().t()
+    got1 = out[m_rows * width:].view(77, 2 * width).double()
+    for got, ref in ((got0, ref0), (got1, ref1)):
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs().max().item()
+        assert err < 5e-5 * max(1.0, ref.abs().max().item()), "max abs err %.3g" % err
