@@ -1,0 +1,331 @@
+"""bench.py — HGTConv forward edges/s on the ogbn-mag-shaped heterograph (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one HGTConv.forward (pyHGT/conv.py:56) over the whole synthetic graph.
+  value     edges/s with every input already resident in HBM and the per-graph plan (CSR) built before the
+            timed region; timed with CUDA events, K steps, max over ranks.
+  e2e       the same metric through the public module call with HOST (pinned) buffers: every step copies
+            node features + node_type + edge_index + edge_type host->device, rebuilds the plan, runs the
+            forward and copies the [N,d] result device->host.
+  roofline  fused edge kernel (csrc/edge.cu): algorithmic bytes per launch / CUDA-event duration of that
+            launch on its own stream, against the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle port (oracle/hgt_oracle.py: the reference's per-triple algorithm) timed on the
+            host cores on a bounded sample (the same generator at a reduced scale), edges/s.
+N > 1: destination-node sharding (pyhgt_b200/sharded.py), one NCCL all-to-all of halo source rows per step;
+the total graph is fixed, so scaling is "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "HGTConv fwd edges/sec"
+UNIT = "edges/s"
+D, HEADS, TYPES, RELS = 256, 8, 4, 4
+CPU_SAMPLE_SCALE = 0.05          # ogbn-mag-shaped x0.05: ~1.06 M edges (the reference needs ~6 GB per 1 M edges)
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def edge_algorithmic_bytes(n_edges, n_dst, d, use_rte=False):
+    """E*(2*d*4 [K'|V' row] + 4 [kv_row]) + N_dst*(d*4 [Q] + d*4 [agg] + 4 [row_ptr])."""
+    per_edge = 2 * d * 4 + 4 + (4 if use_rte else 0)
+    return n_edges * per_edge + n_dst * (2 * d * 4 + 4)
+
+
+def run_cpu_port(steps, warmup, scale=CPU_SAMPLE_SCALE):
+    """Time the CPU oracle port (the reference's algorithm) on a bounded sample; returns (edges/s, info)."""
+    import torch
+    from oracle import hgt_oracle
+    from pyhgt_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = synth.make_mag_shaped(scale)
+    params = hgt_oracle.init_params(D, D, TYPES, RELS, HEADS, use_norm=True, use_RTE=False, seed=0)
+    x = torch.randn(g.num_nodes, D, generator=torch.Generator().manual_seed(0))
+    kw = dict(num_types=TYPES, num_relations=RELS, n_heads=HEADS, use_norm=True, use_RTE=False)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index, g.edge_type, None, **kw)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    eps = g.num_edges * len(times) / total
+    info = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "ogbn-mag-shaped x%g (N=%d, E=%d, d=%d, H=%d), %d timed forwards of oracle/hgt_oracle.py:"
+                      "hgt_forward_ref_port (torch %d threads), %.1f s" % (scale, g.num_nodes, g.num_edges, D, HEADS,
+                                                                           len(times), torch.get_num_threads(), total)}
+    return eps, info, total / len(times) * 1e3, g
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = 1
+    eps, info, ms, g = run_cpu_port(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c2 ogbn-mag-shaped (bounded CPU sample x%g: N=%d, E=%d), d=256, n_heads=8, "
+                                   "4 types / 4 relations, use_norm, no RTE" % (CPU_SAMPLE_SCALE, g.num_nodes,
+                                                                               g.num_edges)},
+            "cpu_baseline": info,
+            "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from pyhgt_b200 import HGTConv, synth, _lib
+    from pyhgt_b200 import plan as hplan
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = synth.make_mag_shaped(args.scale)
+    E, N = g.num_edges, g.num_nodes
+    torch.manual_seed(0)
+    conv = HGTConv(D, D, TYPES, RELS, HEADS, 0.2, True, False).to(dev).eval()
+    HGTConv.keep_att = False        # att [E,H] materialisation is opt-in; not part of the metric
+    gen = torch.Generator().manual_seed(0)
+    x_host = torch.randn(N, D, generator=gen)
+    hbm_peak, peak_src = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world == 1:
+        x = x_host.to(dev)
+        nt, ei, et = g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev)
+
+        def step():
+            return conv(x, nt, ei, et)
+        n_dst_local, e_local = N, E
+        h2d = d2h = 0
+    else:
+        from pyhgt_b200 import sharded
+        shard = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, None, TYPES, RELS, rank, world, dev)
+        x_own = x_host[shard.owned_global].to(dev)
+
+        def step():
+            return shard.forward(conv, x_own)
+        n_dst_local, e_local = shard.n_owned, shard.n_local_edges
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        HGTConv.event_sink = []
+        launches0 = _lib.kernel_launches()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+        launches = _lib.kernel_launches() - launches0
+        ms_total = ev0.elapsed_time(ev1)
+        edge_ms = [a.elapsed_time(b) for (_, a, b) in HGTConv.event_sink]
+        HGTConv.event_sink = None
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = t.item() / args.steps
+        value = E / (ms_step * 1e-3)
+
+        # ---- roofline of the fused edge kernel (this rank's launches) ----
+        edge_avg_ms = sum(edge_ms) / max(len(edge_ms), 1)
+        alg = edge_algorithmic_bytes(e_local, n_dst_local, D)
+        achieved = alg / (edge_avg_ms * 1e-3) / 1e9 if edge_avg_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "edge_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch_c2") if world == 1 and args.scale == 1.0 else None
+        except Exception:
+            pass
+        roofline = {"kernel": "k_edge_fwd_tma (csrc/edge.cu)", "bound": "hbm", "achieved": achieved,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": edge_avg_ms,
+                    "share_of_step": edge_avg_ms / ms_step if ms_step else None}
+
+        # ---- end to end through the module call with host buffers (N = 1 path; sharded: owned rows) ----
+        e2e = None
+        if world == 1:
+            xp = x_host.pin_memory()
+            ntp, eip, etp = g.node_type.pin_memory(), g.edge_index.pin_memory(), g.edge_type.pin_memory()
+            outp = torch.empty((N, D), dtype=torch.float32).pin_memory()
+            h2d = xp.numel() * 4 + ntp.numel() * 8 + eip.numel() * 8 + etp.numel() * 8
+            d2h = outp.numel() * 4
+
+            def e2e_step():
+                xd = xp.to(dev, non_blocking=True)
+                ntd, eid, etd = ntp.to(dev, non_blocking=True), eip.to(dev, non_blocking=True), etp.to(dev, non_blocking=True)
+                o = conv(xd, ntd, eid, etd)                      # new tensors -> the plan is rebuilt inside
+                outp.copy_(o, non_blocking=True)
+            for _ in range(2):
+                e2e_step()
+            torch.cuda.synchronize()
+            k2 = max(3, min(args.steps, 10))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(k2):
+                e2e_step()
+            b.record()
+            torch.cuda.synchronize()
+            e2e_ms = a.elapsed_time(b) / k2
+            e2e = {"value": E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_ms, "includes": "H2D of node_inp/node_type/edge_index/edge_type from pinned "
+                   "host memory, plan (CSR) build, forward, D2H of out [N,d]"}
+        else:
+            xp = x_host[shard.owned_global].pin_memory()
+            outp = torch.empty((shard.n_owned, D), dtype=torch.float32).pin_memory()
+            h2d, d2h = xp.numel() * 4, outp.numel() * 4
+
+            def e2e_step():
+                o = shard.forward(conv, xp.to(dev, non_blocking=True))
+                outp.copy_(o, non_blocking=True)
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            k2 = max(3, min(args.steps, 10))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(k2):
+                e2e_step()
+            b.record()
+            barrier()
+            t2 = torch.tensor([a.elapsed_time(b) / k2], device=dev, dtype=torch.float64)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            e2e = {"value": E / (t2.item() * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                   "d2h_bytes_per_step": d2h * world, "ms_per_step": t2.item(),
+                   "includes": "per rank: H2D of owned node_inp rows from pinned host memory, halo all-to-all, "
+                               "forward, D2H of owned out rows (graph shard plan resident)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu, _, _ = run_cpu_port(steps=3, warmup=1)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "c2 ogbn-mag-shaped: 4 node types / 4 relations, N=%d, E=%d, d=%d, n_heads=%d, "
+                                       "use_norm, no RTE, eval/no_grad%s" % (N, E, D, HEADS,
+                                                                             "" if args.scale == 1.0 else " (scale %g)" % args.scale),
+                           "l2": "inputs exceed L2: node features %.2f GB and [K'|V'] table >> 126 MB; no flush needed"
+                                 % (N * D * 4 / 1e9),
+                           "plan": "destination-sorted CSR built once before the timed region (value); rebuilt every "
+                                   "step in e2e",
+                           "parallelism": "single GPU" if world == 1 else
+                                          "dst-node sharding x%d, one NCCL all-to-all of halo source rows per step" % world,
+                           "linear": "tcgen05 split-bf16 (3 products, fp32 accumulate)", "edge": "TMA bulk-copy ring"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="graph scale (1.0 = BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d bench.py ...)"
+                             % (args.gpus, args.gpus))
+    main_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,8 @@ extern "C" {
 
 const char* hgt_last_error(void);
 int hgt_abi_version(void);
+/* Number of CUDA kernels this library has launched so far in this process (diagnostics / bench.py). */
+uint64_t hgt_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph ingest: int64 COO (the tensors pyHGT/data.py:251-256 `to_torch` emits) -> plan arrays.
@@ -172,11 +174,14 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
  * (eps 1e-5, affine) iff use_norm; rows of out-of-range type are written as zeros (conv.py:120).
  *   o [N,d] rank order (a_linear output, after dropout if training);  x [N,d] rank order;
  *   type_row0 [T+2] int32 prefix of type_count;  norm_w/norm_b [T,d] or NULL;  perm NULL if identity;
+ *   type_active [T] int32 or NULL: when given, only the first type_active[t] rows of type t are written
+ *   (sharded runs: the remaining rows are halo sources that need no output);
  *   out [N,d] in ORIGINAL node order.
  * ---------------------------------------------------------------------------------------------- */
 int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
                         const float* skip, const float* norm_w, const float* norm_b,
-                        const int32_t* perm, int64_t n_nodes, int32_t d, float* out, void* stream);
+                        const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
+                        float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@ SIGNATURES = {
     "hgt_edge_workspace_bytes": [_i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p, _p,
                          _p, _sz, _i32, _p],
-    "hgt_update_epilogue": [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p],
+    "hgt_update_epilogue": [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p],
 }
 
 LIN_GROUP_DTYPE = np.dtype([("a_row0", "<i8"), ("m", "<i8"), ("w_row0", "<i4"), ("n_cblocks", "<i4"),
@@ -64,6 +64,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
         fn.restype = _c.c_int
         fn.argtypes = args
+    lib.hgt_kernel_launches.restype = _c.c_uint64
+    lib.hgt_kernel_launches.argtypes = []
     _lib = lib
     return lib
 
@@ -77,6 +79,10 @@ def check(rc, what):
 def call(name, *args):
     lib = load()
     check(getattr(lib, name)(*args), name)
+
+
+def kernel_launches():
+    return int(load().hgt_kernel_launches())
 
 
 def ptr(t):

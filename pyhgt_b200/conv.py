@@ -78,6 +78,7 @@ class HGTConv(nn.Module):
     keep_att = True            # materialise self.att [E,H] like the reference (conv.py:108)
     edge_variant = 0           # 0 auto, 1 register gather, 2 bulk-copy ring (see csrc/edge.cu)
     linear_impl = 0            # 0 auto, 1 fp32 SIMT, 2 tcgen05
+    event_sink = None          # bench.py: list receiving (stage, start_event, end_event) on the launch stream
 
     def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
                  use_RTE=True, **kwargs):
@@ -164,7 +165,8 @@ class HGTConv(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------
-    def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save):
+    def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
+                      active_per_type=None):
         dev = node_inp.device
         d_in, d = self.in_dim, self.out_dim
         H, T, R = self.n_heads, self.num_types, self.num_relations
@@ -173,7 +175,7 @@ class HGTConv(nn.Module):
         N, E, P = plan.n_nodes, plan.n_edges, plan.n_pairs
         if node_inp.shape[0] != N:
             raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
-        lt = _plan.layer_tables(plan, d_in, d)
+        lt = _plan.layer_tables(plan, d_in, d, active_per_type)
         f32 = dict(dtype=torch.float32, device=dev)
         x = node_inp.contiguous()
         if plan.sorted_types:
@@ -220,11 +222,18 @@ class HGTConv(nn.Module):
         g_act = torch.empty((N, d), **f32)
         att = torch.empty((E, H), **f32) if want_att else None
         stats = torch.empty((N, 2 * H), **f32) if save else None
+        ev0 = ev1 = None
+        if HGTConv.event_sink is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.call("hgt_edge_forward", q_tab.data_ptr(), kv_tab.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
                   plan.kv_row.data_ptr(), _lib.ptr(plan.rte_row) if self.use_RTE else None,
                   plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, N, E, d, H,
                   0 if save else 1, g_act.data_ptr(), _lib.ptr(att), _lib.ptr(stats), ws.data_ptr(), ws.numel(),
                   self.edge_variant, st)
+        if ev0 is not None:
+            ev1.record()
+            HGTConv.event_sink.append(("edge", ev0, ev1))
 
         # 4. typed output linear (conv.py:125) + gated skip + LayerNorm (conv.py:129-133)
         agg = None
@@ -247,7 +256,8 @@ class HGTConv(nn.Module):
         out = torch.empty((N, d), **f32)
         _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
                   self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
-                  None if plan.sorted_types else plan.perm.data_ptr(), N, d, out.data_ptr(), st)
+                  None if plan.sorted_types else plan.perm.data_ptr(), _lib.ptr(lt.type_active_dev), N, d,
+                  out.data_ptr(), st)
         saved = None
         if save:
             saved = dict(plan=plan, lt=lt, x_sorted=x_sorted, w_cat=w_cat, proj=proj, kvr=kvr, agg=agg, o=o,

@@ -29,7 +29,12 @@ int hgt_sm_count();
     }                                                                                             \
   } while (0)
 
-#define HGT_LAUNCH_CHECK() HGT_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_hgt_launches;   // kernels launched by this library (bench.py reports it)
+#define HGT_LAUNCH_CHECK()                  \
+  do {                                      \
+    ++g_hgt_launches;                       \
+    HGT_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline size_t hgt_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -10,14 +10,15 @@ constexpr int kMaxPerLane = 32;   // d <= 1024
 __global__ void __launch_bounds__(256)
 k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
                   int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
-                  const float* __restrict__ norm_b, const int32_t* __restrict__ perm, int64_t n_nodes, int d,
-                  float* __restrict__ out) {
+                  const float* __restrict__ norm_b, const int32_t* __restrict__ perm,
+                  const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   // node type of this rank: types are contiguous in rank order, T is small
   int t = 0;
   while (t < T && row >= type_row0[t + 1]) ++t;
+  if (type_active && t < T && row - type_row0[t] >= type_active[t]) return;   // halo source: no output row
   float* orow = out + (perm ? (int64_t)perm[row] : row) * d;
   if (t >= T) {                                  // type outside [0,T): the reference leaves zeros (conv.py:120)
     for (int c = lane; c < d; c += 32) orow[c] = 0.f;
@@ -72,7 +73,8 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
 
 extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
                                    const float* skip, const float* norm_w, const float* norm_b,
-                                   const int32_t* perm, int64_t n_nodes, int32_t d, float* out, void* stream_) {
+                                   const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
+                                   float* out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(d >= 1 && d <= 32 * kMaxPerLane, "hgt_update_epilogue: d=%d unsupported (max %d)", d,
               32 * kMaxPerLane);
@@ -81,7 +83,7 @@ extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t
   const int warps_per_block = 8;
   unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
   k_update_epilogue<<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, num_types, skip, norm_w, norm_b,
-                                                           perm, n_nodes, d, out);
+                                                           perm, type_active, n_nodes, d, out);
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -231,6 +231,7 @@ class LayerTables:
     q_off: int                    # element offsets inside the projection buffer
     kv_off: int
     proj_elems: int
+    type_active_dev: torch.Tensor = None
 
 
 def _pack_groups(groups, cblocks, dev):
@@ -245,8 +246,10 @@ def _pack_groups(groups, cblocks, dev):
     return (g_dev, g, len(groups), c_dev)
 
 
-def layer_tables(plan, d_in, d_out):
-    key = (d_in, d_out)
+def layer_tables(plan, d_in, d_out, active=None):
+    """`active[t]` (sharded runs): only the first active[t] nodes of type t (in rank order) are destinations
+    that need Q / a_linear / update; the rest of the type (halo sources) only get K'/V' rows."""
+    key = (d_in, d_out, None if active is None else tuple(active))
     hit = plan._layer_tables.get(key)
     if hit is not None:
         return hit
@@ -265,17 +268,27 @@ def layer_tables(plan, d_in, d_out):
     kv_off = (N * d_out + 31) // 32 * 32                   # keep the KV table 128-byte aligned
     proj_elems = kv_off + (plan.kv_rows + 1) * 2 * d_out
     groups, cblocks = [], []
+    act = [plan.type_count[t] if active is None else min(int(active[t]), plan.type_count[t]) for t in range(T)]
     for t in range(T):
         m = plan.type_count[t]
         if m == 0:
             continue
-        first = len(cblocks)
-        cblocks.append((q_off + plan.type_row0[t] * d_out, d_out))
-        for p in pairs_of_type[t]:
-            base = kv_off + plan.pair_row0[p] * 2 * d_out
-            cblocks.append((base, 2 * d_out))
-            cblocks.append((base + d_out, 2 * d_out))
-        groups.append((plan.type_row0[t], m, q_row0[t], 1 + 2 * len(pairs_of_type[t]), first, 1))
+        a = act[t]
+        if a > 0:
+            first = len(cblocks)
+            cblocks.append((q_off + plan.type_row0[t] * d_out, d_out))
+            for p in pairs_of_type[t]:
+                base = kv_off + plan.pair_row0[p] * 2 * d_out
+                cblocks.append((base, 2 * d_out))
+                cblocks.append((base + d_out, 2 * d_out))
+            groups.append((plan.type_row0[t], a, q_row0[t], 1 + 2 * len(pairs_of_type[t]), first, 1))
+        if m - a > 0 and pairs_of_type[t]:
+            first = len(cblocks)
+            for p in pairs_of_type[t]:
+                base = kv_off + (plan.pair_row0[p] + a) * 2 * d_out
+                cblocks.append((base, 2 * d_out))
+                cblocks.append((base + d_out, 2 * d_out))
+            groups.append((plan.type_row0[t] + a, m - a, q_row0[t] + d_out, 2 * len(pairs_of_type[t]), first, 1))
     proj = _pack_groups(groups, cblocks, dev)
     groups, cblocks = [], []
     for p in range(P):
@@ -287,16 +300,17 @@ def layer_tables(plan, d_in, d_out):
     rte = _pack_groups(groups, cblocks, dev)
     groups, cblocks = [], []
     for t in range(T):
-        m = plan.type_count[t]
+        m = act[t]
         if m == 0:
             continue
         groups.append((plan.type_row0[t], m, t * d_out, 1, len(cblocks), 1))
         cblocks.append((plan.type_row0[t] * d_out, d_out))
     upd = _pack_groups(groups, cblocks, dev)
     rt_group = _pack_groups([(0, RTE_MAX_LEN, 0, 1, 0, 1)], [(0, d_in)], dev)
-    small = torch.tensor(q_row0 + (cat_row0 if P else [0]), dtype=torch.int32).to(dev)
+    small = torch.tensor(q_row0 + (cat_row0 if P else [0]) + act, dtype=torch.int32).to(dev)
     lt = LayerTables(cat_rows=rows, q_row0=q_row0, cat_row0=cat_row0, q_row0_dev=small[:T],
-                     cat_row0_dev=small[T:], proj_groups=proj, rte_groups=rte, upd_groups=upd, rt_group=rt_group, q_off=q_off,
+                     cat_row0_dev=small[T:T + max(P, 1)],
+                     type_active_dev=None if active is None else small[T + max(P, 1):], proj_groups=proj, rte_groups=rte, upd_groups=upd, rt_group=rt_group, q_off=q_off,
                      kv_off=kv_off, proj_elems=proj_elems)
     plan._layer_tables[key] = lt
     return lt
