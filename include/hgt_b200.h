@@ -169,6 +169,17 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      float* agg_out, float* att_out, float* stats_out,
                      void* workspace, size_t workspace_bytes, int32_t variant, void* stream);
 
+/* Backward of hgt_edge_forward (training; the reference differentiates the same ops with autograd,
+ * OAG/train_paper_field.py:249).  Inputs: the forward's q / kv / kvr tables, its un-activated output
+ * `agg` (apply_gelu = 0), the saved per-destination softmax statistics `stats` [N,2H] and the incoming
+ * gradient `dagg` [N,d].  Outputs (all must be ZERO-initialised by the caller): dq [N,d],
+ * dkv [rows+1,2d] (gradient of the [K'|V'] table; the last row belongs to the all-zero row and is to be
+ * discarded), dkvr [P*240+1,2d] or NULL.  workspace: >= 256 bytes. */
+int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const float* agg, const float* dagg,
+                      const float* stats, const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
+                      const int32_t* tiles, int32_t n_tiles, int64_t n_nodes, int32_t d, int32_t n_heads,
+                      float* dq, float* dkv, float* dkvr, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Update epilogue (conv.py:129-133): y = o*sigmoid(skip[t]) + x*(1-sigmoid(skip[t])); LayerNorm_t(y)
  * (eps 1e-5, affine) iff use_norm; rows of out-of-range type are written as zeros (conv.py:120).

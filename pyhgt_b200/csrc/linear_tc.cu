@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -129,7 +131,7 @@ k_typed_linear_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                   const hgt_lin_cblock* __restrict__ cblocks, float* __restrict__ out, TcTilePrefix tp) {
   extern __shared__ unsigned char smem_dyn[];
   // carve: [stages][A 16 KB | B BN*128 B] (1024-aligned), then barriers, tmem pointer, bias tile
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);   // keeps the shared address space
   const uint32_t a_bytes = TC_BM * TC_BK * 2;
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t b_bytes_al = (b_bytes + 1023) & ~1023u;
@@ -266,6 +268,239 @@ k_typed_linear_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
 }
 
+
+// ---- W-stationary persistent GEMM (default) -------------------------------------------------------
+// A "unit" = one column task (group, column block, n-tile of BN columns) x a chunk of up to MCH m-tiles.
+// The CTA keeps the column task's W_hi / W_lo tiles (all K) resident in shared memory, streams the A_hi / A_lo
+// k-blocks of successive m-tiles through a ring, and issues per k-block the three products
+// A_hi*W_hi + A_hi*W_lo + A_lo*W_hi into a double-buffered TMEM accumulator, so the epilogue of m-tile i
+// overlaps the MMAs of m-tile i+1.  Units are ordered m-chunk-major so that CTAs running concurrently read the
+// same A rows from L2 with different W.  L2->SM traffic per output tile drops from 384 KB (tile-per-CTA kernel
+// below) to 128 KB (+ W amortised over the chunk).
+static int tc2_mch() { static int v = [] { const char* e = getenv("HGT_TC_MCH"); int x = e ? atoi(e) : 8; return x < 1 ? 1 : x; }(); return v; }
+static int tc2_stage_cap() { static int v = [] { const char* e = getenv("HGT_TC_STAGES"); int x = e ? atoi(e) : 8; return x < 2 ? 2 : x; }(); return v; }
+constexpr int TC2_THREADS = 192;
+constexpr int TC2_STG_LD = 20;                 // floats per staged row (16 + 4 pad)
+constexpr int TC2_STAGE_BYTES = 4 * 32 * TC2_STG_LD * 4;
+
+struct Tc2Sched {
+  int32_t first_unit[kMaxGroups + 1];
+  int32_t n_tiles_n;
+};
+
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   const float* __restrict__ bias, int Kp, int cb_width, int BN, int stages, int tmem_cols,
+                   const hgt_lin_group* __restrict__ groups, int n_groups,
+                   const hgt_lin_cblock* __restrict__ cblocks, float* __restrict__ out, Tc2Sched sc, int MCH) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);   // keeps the shared address space
+  const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;                       // one A tile (hi or lo)
+  const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;                // one W tile (hi or lo)
+  const uint32_t b_bytes_al = (b_bytes + 1023) & ~1023u;
+  const uint32_t w_region = (uint32_t)k_blocks * 2 * b_bytes_al;    // resident W
+  const uint32_t a_stage = a_bytes;                                 // one tile per stage: A_hi(kb), A_lo(kb), A_hi(kb+1), ...
+  unsigned char* w_smem = smem;
+  unsigned char* a_smem = smem + w_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)stages * a_stage);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + stages;
+  uint64_t* w_full = bars + 2 * stages;
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* t_full = w_empty + 1;       // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);        // 16-byte aligned: the barrier block is 16*(stages+3) B
+  float* s_stage = s_bias + ((BN + 3) & ~3);                          // [4 warps][32][TC2_STG_LD] epilogue transpose
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = sc.first_unit[n_groups];
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(s_u32(&a_full[s]), 1);
+      mbar_init(s_u32(&a_empty[s]), 1);
+    }
+    mbar_init(s_u32(w_full), 1);
+    mbar_init(s_u32(w_empty), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_u32(&t_full[b]), 1);
+      mbar_init(s_u32(&t_empty[b]), 4);                              // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // unit decode shared by all roles
+  struct Unit { int64_t m_first; int n_mt; int a_row0; int w_row; int64_t m_rows; int64_t out_off; int64_t ld; int n0;
+                int has_bias; };
+  auto decode = [&](int u, Unit& un) {
+    int g = 0;
+    while (g + 1 < n_groups && u >= sc.first_unit[g + 1]) ++g;
+    const hgt_lin_group grp = groups[g];
+    int local = u - sc.first_unit[g];
+    const int ncol = grp.n_cblocks * sc.n_tiles_n;
+    const int chunk = local / ncol;
+    const int col = local - chunk * ncol;
+    const int cb = col / sc.n_tiles_n;
+    const int nt = col - cb * sc.n_tiles_n;
+    const hgt_lin_cblock cblk = cblocks[grp.cb_first + cb];
+    const int64_t mt_total = (grp.m + TC_BM - 1) / TC_BM;
+    un.m_first = (int64_t)chunk * MCH;
+    un.n_mt = (int)min((int64_t)MCH, mt_total - un.m_first);
+    un.a_row0 = (int)grp.a_row0;
+    un.m_rows = grp.m;
+    un.n0 = nt * BN;
+    un.w_row = grp.w_row0 + cb * cb_width + un.n0;
+    un.out_off = cblk.out_off;
+    un.ld = cblk.ld;
+    un.has_bias = grp.has_bias;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t a_it = 0, unit_it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+        Unit un;
+        decode(u, un);
+        mbar_wait(s_u32(w_empty), (unit_it & 1u) ^ 1u);               // previous unit's MMAs are done with W
+        mbar_expect_tx(s_u32(w_full), (uint32_t)k_blocks * 2 * b_bytes);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tma_load_2d(s_u32(w_smem + (size_t)(2 * kb) * b_bytes_al), &map_w_hi, kb * TC_BK, un.w_row, s_u32(w_full));
+          tma_load_2d(s_u32(w_smem + (size_t)(2 * kb + 1) * b_bytes_al), &map_w_lo, kb * TC_BK, un.w_row, s_u32(w_full));
+        }
+        for (int mt = 0; mt < un.n_mt; ++mt) {
+          const int a_row = un.a_row0 + (int)((un.m_first + mt) * TC_BM);
+          for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
+            const int s = a_it % stages;
+            mbar_wait(s_u32(&a_empty[s]), ((a_it / stages) & 1u) ^ 1u);
+            const uint32_t bar = s_u32(&a_full[s]);
+            mbar_expect_tx(bar, a_bytes);
+            tma_load_2d(s_u32(a_smem + (size_t)s * a_stage), (j & 1) ? &map_a_lo : &map_a_hi, (j >> 1) * TC_BK, a_row, bar);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t a_it = 0, unit_it = 0, acc_it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+        Unit un;
+        decode(u, un);
+        mbar_wait(s_u32(w_full), unit_it & 1u);
+        for (int mt = 0; mt < un.n_mt; ++mt, ++acc_it) {
+          const uint32_t buf = acc_it & 1u;
+          mbar_wait(s_u32(&t_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + buf * (uint32_t)BN;
+          for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
+            const int s = a_it % stages;
+            const int kb = j >> 1;
+            mbar_wait(s_u32(&a_full[s]), (a_it / stages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t d_a = make_sw128_desc(s_u32(a_smem + (size_t)s * a_stage));
+            const uint64_t d_whi = make_sw128_desc(s_u32(w_smem + (size_t)(2 * kb) * b_bytes_al));
+            if (!(j & 1)) {
+              // A_hi(kb): A_hi*W_hi + A_hi*W_lo
+              const uint64_t d_wlo = make_sw128_desc(s_u32(w_smem + (size_t)(2 * kb + 1) * b_bytes_al));
+#pragma unroll
+              for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                umma_bf16_ss(tmem_d, d_a + o, d_whi + o, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_ss(tmem_d, d_a + o, d_wlo + o, idesc, 1u);
+              }
+            } else {
+              // A_lo(kb): A_lo*W_hi
+#pragma unroll
+              for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                umma_bf16_ss(tmem_d, d_a + o, d_whi + o, idesc, 1u);
+              }
+            }
+            umma_commit(s_u32(&a_empty[s]));
+          }
+          umma_commit(s_u32(&t_full[buf]));
+        }
+        umma_commit(s_u32(w_empty));
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int et = threadIdx.x - 64;                                 // 0..127 among epilogue threads
+    uint32_t acc_it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      Unit un;
+      decode(u, un);
+      asm volatile("bar.sync 1, 128;" ::: "memory");               // previous unit's bias reads are finished
+      for (int c = et; c < BN; c += 128) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int mt = 0; mt < un.n_mt; ++mt, ++acc_it) {
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t m0 = (un.m_first + mt) * TC_BM;
+        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN;
+        // TMEM gives each lane one ROW; storing that directly would make every STG touch 32 different lines.
+        // Transpose 32x16 blocks through a per-warp staging buffer so that 4 lanes write 64 contiguous bytes of
+        // a row (8 rows, 16 full sectors per store instruction).
+        float* stg = s_stage + (size_t)lg * (32 * TC2_STG_LD);
+        const int sub = lane & 3, rsel = lane >> 2;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_row + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * TC2_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = 8 * k + rsel;                            // row inside this warp's 32-row slab
+            if (m0 + lg * 32 + rr < un.m_rows) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * TC2_STG_LD + sub * 4);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              *reinterpret_cast<float4*>(out + un.out_off + (m0 + lg * 32 + rr) * un.ld + un.n0 + c0 + sub * 4) = v;
+            }
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&t_empty[buf])) : "memory");
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -317,6 +552,8 @@ void extents(const hgt_lin_group* h_groups, int n_groups, int cb_width, int64_t*
 
 }  // namespace
 
+static const bool g_tc_tile_per_cta = [] { const char* e = getenv("HGT_TC_TILE_PER_CTA"); return e && e[0] == '1'; }();
+
 bool hgt_typed_linear_tc_supported(int64_t lda, int32_t K, int32_t cb_width) {
   (void)lda;
   return cb_width % 16 == 0 && pick_bn(cb_width) > 0 && K >= TC_BK;
@@ -361,6 +598,51 @@ int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float
   if ((rc = make_map(&m_w_hi, w_hi, w_rows, Kp, BN))) return rc;
   if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, BN))) return rc;
 
+  const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
+  if (!g_tc_tile_per_cta) {
+    // ---- W-stationary persistent kernel ----
+    int bn = 0;
+    for (int c = 128; c >= 16; c -= 16) {
+      if (cb_width % c) continue;
+      size_t w_region = (size_t)k_blocks * 2 * (((size_t)c * TC_BK * 2 + 1023) & ~(size_t)1023);
+      if (w_region <= 136 * 1024) { bn = c; break; }
+    }
+    if (bn > 0) {
+      const size_t w_region = (size_t)k_blocks * 2 * (((size_t)bn * TC_BK * 2 + 1023) & ~(size_t)1023);
+      const size_t a_stage = (size_t)TC_BM * TC_BK * 2;
+      const size_t misc = 1024 + 256 + (size_t)bn * 4 + 64 + TC2_STAGE_BYTES;
+      int stages = (int)((227 * 1024 - w_region - misc - 1024) / a_stage);
+      if (stages > tc2_stage_cap()) stages = tc2_stage_cap();
+      if (stages >= 2) {
+        Tc2Sched sc;
+        const int mch = tc2_mch();
+        sc.n_tiles_n = cb_width / bn;
+        int64_t units = 0;
+        for (int g = 0; g < n_groups; ++g) {
+          sc.first_unit[g] = (int32_t)units;
+          int64_t mt = (h_groups[g].m + TC_BM - 1) / TC_BM;
+          units += (mt + mch - 1) / mch * h_groups[g].n_cblocks * sc.n_tiles_n;
+          HGT_REQUIRE(units < 2147483647ll, "hgt_typed_linear(tc): too many units");
+        }
+        sc.first_unit[n_groups] = (int32_t)units;
+        if (units == 0) return 0;
+        if ((rc = make_map(&m_w_hi, w_hi, w_rows, Kp, bn))) return rc;
+        if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, bn))) return rc;
+        int tmem_cols = 32;
+        while (tmem_cols < 2 * bn) tmem_cols <<= 1;
+        size_t smem = 1024 + w_region + (size_t)stages * a_stage + (2 * stages + 6) * 8 + 16 + (size_t)bn * 4 + 64 +
+                      TC2_STAGE_BYTES;
+        HGT_CHECK_CUDA(cudaFuncSetAttribute(k_typed_linear_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = hgt_sm_count();
+        if (grid > units) grid = (int)units;
+        k_typed_linear_tc2<<<grid, TC2_THREADS, smem, st>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, bias, Kp, cb_width, bn,
+                                                            stages, tmem_cols, groups, n_groups, cblocks, out, sc, mch);
+        HGT_LAUNCH_CHECK();
+        return 0;
+      }
+    }
+  }
+  // ---- one tile per CTA (fallback for very wide K; HGT_TC_TILE_PER_CTA=1 forces it) ----
   TcTilePrefix tp;
   tp.n_tiles_n = cb_width / BN;
   int64_t total = 0;

@@ -69,6 +69,99 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
   }
 }
 
+// Vectorised variant: d % 4 == 0, each lane owns NV float4 chunks (chunk c = lane + 32*i), 128-bit loads/stores.
+template <int NV>
+__global__ void __launch_bounds__(256)
+k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
+                      int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
+                      const float* __restrict__ norm_b, const int32_t* __restrict__ perm,
+                      const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int nvec = d >> 2;
+  // issue the row loads first; the (short, warp-uniform) type search overlaps with them
+  float4 ov[NV], xv[NV];
+  const float4* op = reinterpret_cast<const float4*>(o + row * d);
+  const float4* xp = reinterpret_cast<const float4*>(x + row * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) { ov[i] = __ldcs(op + c); xv[i] = __ldcs(xp + c); }
+    else { ov[i] = make_float4(0.f, 0.f, 0.f, 0.f); xv[i] = ov[i]; }
+  }
+  int t = 0;
+  while (t < T && row >= type_row0[t + 1]) ++t;
+  if (type_active && t < T && row - type_row0[t] >= type_active[t]) return;
+  float4* orow = reinterpret_cast<float4*>(out + (perm ? (int64_t)perm[row] : row) * d);
+  if (t >= T) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) orow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  const float alpha = 1.0f / (1.0f + __expf(-skip[t]));
+  const float beta = 1.0f - alpha;
+  float4 y[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    y[i].x = ov[i].x * alpha + xv[i].x * beta;
+    y[i].y = ov[i].y * alpha + xv[i].y * beta;
+    y[i].z = ov[i].z * alpha + xv[i].z * beta;
+    y[i].w = ov[i].w * alpha + xv[i].w * beta;
+    sum += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+  }
+  if (norm_w == nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) __stcs(orow + c, y[i]);
+    }
+    return;
+  }
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float mean = sum / d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float a = y[i].x - mean, b = y[i].y - mean, e = y[i].z - mean, f = y[i].w - mean;
+      var += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+  const float rstd = rsqrtf(var / d + 1e-5f);
+  const float4* w = reinterpret_cast<const float4*>(norm_w + (int64_t)t * d);
+  const float4* b = reinterpret_cast<const float4*>(norm_b + (int64_t)t * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 wv = __ldg(w + c), bv = __ldg(b + c);
+      float4 r;
+      r.x = (y[i].x - mean) * rstd * wv.x + bv.x;
+      r.y = (y[i].y - mean) * rstd * wv.y + bv.y;
+      r.z = (y[i].z - mean) * rstd * wv.z + bv.z;
+      r.w = (y[i].w - mean) * rstd * wv.w + bv.w;
+      __stcs(orow + c, r);
+    }
+  }
+}
+
+template <int NV>
+void launch_vec(const float* o, const float* x, const int32_t* type_row0, int T, const float* skip,
+                const float* norm_w, const float* norm_b, const int32_t* perm, const int32_t* type_active,
+                int64_t n_nodes, int d, float* out, cudaStream_t st) {
+  const int warps_per_block = 8;
+  unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
+  k_update_epilogue_vec<NV><<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, T, skip, norm_w, norm_b, perm,
+                                                                  type_active, n_nodes, d, out);
+}
+
 }  // namespace
 
 extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
@@ -80,6 +173,18 @@ extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t
               32 * kMaxPerLane);
   HGT_REQUIRE((norm_w == nullptr) == (norm_b == nullptr), "hgt_update_epilogue: norm_w/norm_b must go together");
   if (n_nodes == 0) return 0;
+  const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(x) |
+                                        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(norm_w) |
+                                        reinterpret_cast<uintptr_t>(norm_b)) % 16 == 0);
+  if (aligned && d <= 1024) {
+    const int nv = (d / 4 + 31) / 32;
+    if (nv <= 1) launch_vec<1>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
+    else if (nv <= 2) launch_vec<2>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
+    else if (nv <= 4) launch_vec<4>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
+    else launch_vec<8>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
+    HGT_LAUNCH_CHECK();
+    return 0;
+  }
   const int warps_per_block = 8;
   unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
   k_update_epilogue<<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, num_types, skip, norm_w, norm_b,

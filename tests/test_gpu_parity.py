@@ -299,3 +299,72 @@ def test_sharded_local_forward_matches_full_graph(world):
             out, _, _ = m._forward_impl(x_local, sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time,
                                         want_att=False, save=False, active_per_type=sh.active_per_type)
         _close(out[:sh.n_owned], full[sh.owned_global], "rank %d/%d owned rows" % (rank, world), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["c1_rte", "rand_t3r4_dk4"])
+def test_backward_matches_reference_autograd(name):
+    """d(sum(out*w))/d{node_inp, every parameter} against the gradients the reference's own autograd produced
+    (tests/golden, oracle/make_golden.py)."""
+    dev = _dev()
+    fx = load_golden(name)
+    m = _module_from_fixture(fx, dev)      # eval(): dropout off, same as the fixture
+    x = fx["node_inp"].to(dev).requires_grad_(True)
+    out = m(x, fx["node_type"].to(dev), fx["edge_index"].to(dev), fx["edge_type"].to(dev), fx["edge_time"].to(dev))
+    _close(out.detach(), fx["out"], name + " training-path out")
+    _close(m.att, fx["att"], name + " training-path att", atol=1e-4)
+    (out * fx["grad_weight"].to(dev)).sum().backward()
+
+    def check(got, ref, what):
+        got, ref = got.float().cpu(), ref.float()
+        scale = ref.abs().max().item()
+        fro = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+        assert torch.allclose(got, ref, rtol=1e-3, atol=1e-3 * max(scale, 1e-6)), \
+            "%s: max abs err %.3g (scale %.3g, rel fro %.3g)" % (what, (got - ref).abs().max().item(), scale, fro)
+        assert fro <= 2e-3, "%s: relative Frobenius error %.3g" % (what, fro)
+
+    check(x.grad, fx["grad_node_inp"], name + " d node_inp")
+    got = {k: p.grad for k, p in m.named_parameters()}
+    for k, ref in fx["grad_params"].items():
+        assert got[k] is not None, "no gradient for %s" % k
+        check(got[k], ref, name + " d " + k)
+
+
+def test_backward_hub_split_and_unsorted_types():
+    """Gradients with hub splitting forced (atomic dq path) equal the unsplit ones; compared against autograd
+    through the CPU oracle port."""
+    import pyhgt_b200
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    g = synth.make_random(200, 1500, 2, 3, seed=31)
+    hub = torch.full((600,), 5, dtype=torch.int64)
+    gen = torch.Generator().manual_seed(3)
+    g.edge_index = torch.cat([g.edge_index, torch.stack([torch.randint(0, 200, (600,), generator=gen), hub])], 1)
+    g.edge_type = torch.cat([g.edge_type, torch.randint(0, 3, (600,), generator=gen)])
+    g.edge_time = torch.cat([g.edge_time, torch.randint(0, 240, (600,), generator=gen)])
+    torch.manual_seed(2)
+    m = pyhgt_b200.HGTConv(32, 32, 2, 3, 4, 0.0, True, True).eval()
+    x = torch.randn(200, 32)
+    w = torch.randn(200, 32)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref, _ = hgt_oracle.hgt_forward_ref_port(params, xr, g.node_type, g.edge_index, g.edge_type, g.edge_time,
+                                             num_types=2, num_relations=3, n_heads=4)
+    (ref * w).sum().backward()
+    m = m.to(dev)
+    old = (P.TILE_SPLIT_EDGES, P.TILE_TARGET_EDGES)
+    try:
+        P.TILE_SPLIT_EDGES, P.TILE_TARGET_EDGES = 50, 8
+        P.clear_plan_cache()
+        xg = x.to(dev).requires_grad_(True)
+        out = m(xg, g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev), g.edge_time.to(dev))
+        (out * w.to(dev)).sum().backward()
+    finally:
+        P.TILE_SPLIT_EDGES, P.TILE_TARGET_EDGES = old
+        P.clear_plan_cache()
+    _close(out.detach(), ref.detach(), "hub training out")
+    for got, exp, what in [(xg.grad, xr.grad, "d node_inp")] + \
+            [(p.grad, params[k].grad, "d " + k) for k, p in m.named_parameters() if params[k].grad is not None]:
+        got, exp = got.cpu(), exp
+        scale = max(exp.abs().max().item(), 1e-6)
+        assert torch.allclose(got, exp, rtol=2e-3, atol=2e-3 * scale), \
+            "%s: max abs err %.3g (scale %.3g)" % (what, (got - exp).abs().max().item(), scale)
