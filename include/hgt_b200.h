@@ -83,11 +83,13 @@ int hgt_plan_edges_fill(const int64_t* edge_index, const int64_t* edge_type, con
  * tiles whose partial (max, sum, acc) are merged afterwards.
  *   tiles [max_tiles,4] int32 = {dst_begin, dst_end, edge_begin, edge_end}; for a split destination
  *   the second field is -(partial_slot+1) < 0 and [edge_begin, edge_end) is a sub-range of its segment.
- *   n_tiles [2] int32 = {number of tiles, number of split (partial) tiles}.
- * Synchronises the stream (returns the counts to the host through h_n_tiles[2]). */
+ *   hubs [max_hubs,4] int32 = {dst, first partial slot, pieces, 0} for every split destination;
+ *   n_tiles [3] int32 = {number of tiles, number of split (partial) tiles, number of hubs}.
+ * Synchronises the stream (returns the counts to the host through h_n_tiles[3]). */
 int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges,
                    int32_t target_edges, int32_t split_edges,
-                   int32_t* tiles, int64_t max_tiles, int32_t* d_n_tiles, int32_t* h_n_tiles,
+                   int32_t* tiles, int64_t max_tiles, int32_t* hubs, int64_t max_hubs,
+                   int32_t* d_n_tiles, int32_t* h_n_tiles,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[k,:] = in[perm[k],:]  (rows of `width` floats); used only when node_type is not pre-sorted. */
@@ -156,7 +158,7 @@ int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* b
 /*  q       [N, d]        rank order, Q[i] = W_q^{type(i)} x_i + b
  *  kv      [rows+1, 2d]  row = [K' | V'] of <source node, relation>; last row all zero
  *  kvr     [P*240+1, 2d] RTE contribution per <pair, dt> (NULL when !use_RTE); last row all zero
- *  tiles   from hgt_plan_tiles;  partial workspace: n_split * (2*H + d) floats
+ *  tiles / hubs from hgt_plan_tiles;  partial workspace: n_split * (2*H + d) floats
  *  agg_out [N, d]  gelu(sum_e att[e] * V'[e]) if apply_gelu else the raw sum   (conv.py:119)
  *  att_out [E, H]  softmax weights in ORIGINAL edge order (conv.py:108 `self.att`) or NULL
  *  stats_out [N, 2H] per-destination (max, sum) per head, or NULL (kept for the backward pass)
@@ -165,6 +167,7 @@ int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_t n_heads, 
 int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
                      const int32_t* csr_eid, const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles,
+                     const int32_t* hubs, int32_t n_hubs,
                      int64_t n_nodes, int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu,
                      float* agg_out, float* att_out, float* stats_out,
                      void* workspace, size_t workspace_bytes, int32_t variant, void* stream);

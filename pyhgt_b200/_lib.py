@@ -24,7 +24,7 @@ SIGNATURES = {
     "hgt_plan_nodes": [_p, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p],
     "hgt_plan_edges_sort": [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p],
     "hgt_plan_edges_fill": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p],
-    "hgt_plan_tiles": [_p, _i64, _i64, _i32, _i32, _p, _i64, _p, _c.POINTER(_i32), _p, _sz, _p],
+    "hgt_plan_tiles": [_p, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _c.POINTER(_i32), _p, _sz, _p],
     "hgt_gather_rows": [_p, _p, _i64, _i32, _p, _p],
     "hgt_fold_weights": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
                          _p, _p, _p],
@@ -32,8 +32,8 @@ SIGNATURES = {
     "hgt_typed_linear_workspace_bytes": [_p, _i32, _i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_typed_linear": [_p, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _sz, _p],
     "hgt_edge_workspace_bytes": [_i32, _i32, _i32, _c.POINTER(_sz)],
-    "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p, _p,
-                         _p, _sz, _i32, _p],
+    "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p,
+                         _p, _p, _sz, _i32, _p],
     "hgt_edge_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _sz, _p],
     "hgt_update_epilogue": [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p],
 }

@@ -228,7 +228,7 @@ class HGTConv(nn.Module):
             ev0.record()
         _lib.call("hgt_edge_forward", q_tab.data_ptr(), kv_tab.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
                   plan.kv_row.data_ptr(), _lib.ptr(plan.rte_row) if self.use_RTE else None,
-                  plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, N, E, d, H,
+                  plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, E, d, H,
                   0 if save else 1, g_act.data_ptr(), _lib.ptr(att), _lib.ptr(stats), ws.data_ptr(), ws.numel(),
                   self.edge_variant, st)
         if ev0 is not None:

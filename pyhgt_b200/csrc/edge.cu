@@ -454,55 +454,72 @@ k_edge_fwd_tma(EdgeParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// merge of hub pieces: one warp per hub (the warp whose piece starts the hub's segment)
+// merge of hub pieces: one 1024-thread CTA per hub (hub list from hgt_plan_tiles).  The (max, sum, acc)
+// partials of a hub's pieces are combined with the usual log-sum-exp rescaling; pieces are spread over the
+// 32 warps so a hub cut into thousands of pieces (power-law graphs) still merges in microseconds.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_merge_partials(EdgeParams p, int n_split) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  // split tiles are not contiguous in the tile table; scan the table for pieces that start a hub
-  for (int tile = gw; tile < p.n_tiles; tile += (gridDim.x * blockDim.x) >> 5) {
-    const int4 tl = reinterpret_cast<const int4*>(p.tiles)[tile];
-    if (tl.y >= 0) continue;
-    const int dst = tl.x;
-    const int seg_begin = p.row_ptr[dst], seg_end = p.row_ptr[dst + 1];
-    if (tl.z != seg_begin) continue;                       // not the first piece of this hub
-    const int slot0 = -tl.y - 1;
-    int pieces = 0;
-    while (tile + pieces < p.n_tiles) {
-      const int4 t2 = reinterpret_cast<const int4*>(p.tiles)[tile + pieces];
-      if (t2.y >= 0 || t2.x != dst) break;
-      ++pieces;
+constexpr int kMergeThreads = 1024;
+
+__global__ void __launch_bounds__(kMergeThreads)
+k_merge_partials(EdgeParams p, const int32_t* __restrict__ hubs, int n_hubs) {
+  __shared__ float s_M[32], s_L[32], s_inv[32];
+  __shared__ float s_red[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stride = 2 * p.H + p.d;
+  for (int hb = blockIdx.x; hb < n_hubs; hb += gridDim.x) {
+    const int dst = hubs[4 * hb], slot0 = hubs[4 * hb + 1], pieces = hubs[4 * hb + 2];
+    const float* part = p.partial + (int64_t)slot0 * stride;
+    // per head: M = max_k m_k, then L = sum_k l_k * exp(m_k - M)
+    for (int h = warp; h < p.H; h += 32) {
+      float mx = -INFINITY;
+      for (int k = lane; k < pieces; k += 32) mx = fmaxf(mx, part[(int64_t)k * stride + h]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float l = 0.f;
+      for (int k = lane; k < pieces; k += 32) {
+        const float* w = part + (int64_t)k * stride;
+        l += w[p.H + h] * __expf(w[h] - mx);
+      }
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      if (lane == 0) { s_M[h] = mx; s_L[h] = l; s_inv[h] = 1.0f / (l + 1e-16f); }
     }
-    const int stride = 2 * p.H + p.d;
-    for (int h = 0; h < p.H; ++h) {
-      float M = -INFINITY;
-      for (int k = 0; k < pieces; ++k) M = fmaxf(M, p.partial[(int64_t)(slot0 + k) * stride + h]);
-      float L = 0.f;
-      for (int k = 0; k < pieces; ++k) {
-        const float* w = p.partial + (int64_t)(slot0 + k) * stride;
-        L += w[p.H + h] * __expf(w[h] - M);
-      }
-      const float inv = 1.0f / (L + 1e-16f);
-      for (int c = lane; c < p.DK; c += 32) {
-        float a = 0.f;
-        for (int k = 0; k < pieces; ++k) {
-          const float* w = p.partial + (int64_t)(slot0 + k) * stride;
-          a += w[2 * p.H + h * p.DK + c] * __expf(w[h] - M);
-        }
-        a *= inv;
-        p.agg_out[(int64_t)dst * p.d + h * p.DK + c] = p.apply_gelu ? hgt_gelu_erf(a) : a;
-      }
-      if (p.stats_out && lane == 0) {
-        p.stats_out[(int64_t)dst * 2 * p.H + h] = M;
-        p.stats_out[(int64_t)dst * 2 * p.H + p.H + h] = L;
-      }
-      if (p.att_out) {
-        for (int c = seg_begin + lane; c < seg_end; c += 32) {
-          float* a = p.att_out + (int64_t)p.csr_eid[c] * p.H + h;
-          *a = __expf(*a - M) * inv;
+    __syncthreads();
+    // columns in chunks of 32; warp w accumulates the pieces k = w, w+32, ...
+    for (int c0 = 0; c0 < p.d; c0 += 32) {
+      const int c = c0 + lane;
+      float a = 0.f;
+      if (c < p.d) {
+        const int h = c / p.DK;
+        const float M = s_M[h];
+        for (int k = warp; k < pieces; k += 32) {
+          const float* w = part + (int64_t)k * stride;
+          a = fmaf(w[2 * p.H + c], __expf(w[h] - M), a);
         }
       }
+      s_red[warp][lane] = a;
+      __syncthreads();
+      if (warp == 0 && c < p.d) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) t += s_red[w][lane];
+        t *= s_inv[c / p.DK];
+        p.agg_out[(int64_t)dst * p.d + c] = p.apply_gelu ? hgt_gelu_erf(t) : t;
+      }
+      __syncthreads();
     }
+    if (p.stats_out && threadIdx.x < p.H) {
+      p.stats_out[(int64_t)dst * 2 * p.H + threadIdx.x] = s_M[threadIdx.x];
+      p.stats_out[(int64_t)dst * 2 * p.H + p.H + threadIdx.x] = s_L[threadIdx.x];
+    }
+    if (p.att_out) {
+      const int seg_begin = p.row_ptr[dst], seg_end = p.row_ptr[dst + 1];
+      const int64_t n = (int64_t)(seg_end - seg_begin) * p.H;
+      for (int64_t i = threadIdx.x; i < n; i += kMergeThreads) {
+        const int c = seg_begin + (int)(i / p.H), h = (int)(i % p.H);
+        float* a = p.att_out + (int64_t)p.csr_eid[c] * p.H + h;
+        *a = __expf(*a - s_M[h]) * s_inv[h];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -541,7 +558,8 @@ extern "C" int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_
 
 extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kvr, const int32_t* row_ptr,
                                 const int32_t* kv_row, const int32_t* rte_row, const int32_t* csr_eid,
-                                const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles, int64_t n_nodes,
+                                const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles, const int32_t* hubs,
+                                int32_t n_hubs, int64_t n_nodes,
                                 int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu, float* agg_out,
                                 float* att_out, float* stats_out, void* workspace, size_t workspace_bytes,
                                 int32_t variant, void* stream_) {
@@ -606,7 +624,8 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
   else rc = dispatch_nch<1>(p, nch, variant, grid, smem, st);
   if (rc) return rc;
   if (n_split_tiles > 0) {
-    k_merge_partials<<<sms, 128, 0, st>>>(p, n_split_tiles);
+    HGT_REQUIRE(hubs != nullptr && n_hubs > 0, "hgt_edge_forward: split tiles present but no hub list given");
+    k_merge_partials<<<n_hubs < 4 * sms ? n_hubs : 4 * sms, kMergeThreads, 0, st>>>(p, hubs, n_hubs);
     HGT_LAUNCH_CHECK();
   }
   return 0;

@@ -601,17 +601,21 @@ int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float
   const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
   if (!g_tc_tile_per_cta) {
     // ---- W-stationary persistent kernel ----
-    int bn = 0;
+    // widest n-tile whose resident W (all K, hi + lo) still leaves room for >= 4 A stages of 16 KB
+    const size_t a_stage = (size_t)TC_BM * TC_BK * 2;
+    int bn = 0, stages = 0;
+    size_t w_region = 0;
     for (int c = 128; c >= 16; c -= 16) {
       if (cb_width % c) continue;
-      size_t w_region = (size_t)k_blocks * 2 * (((size_t)c * TC_BK * 2 + 1023) & ~(size_t)1023);
-      if (w_region <= 136 * 1024) { bn = c; break; }
+      const size_t wr = (size_t)k_blocks * 2 * (((size_t)c * TC_BK * 2 + 1023) & ~(size_t)1023);
+      const size_t misc = 1024 + 256 + (size_t)c * 4 + 64 + TC2_STAGE_BYTES + 1024;
+      if (wr + misc + 4 * a_stage > 227 * 1024) continue;
+      bn = c;
+      w_region = wr;
+      stages = (int)((227 * 1024 - wr - misc) / a_stage);
+      break;
     }
     if (bn > 0) {
-      const size_t w_region = (size_t)k_blocks * 2 * (((size_t)bn * TC_BK * 2 + 1023) & ~(size_t)1023);
-      const size_t a_stage = (size_t)TC_BM * TC_BK * 2;
-      const size_t misc = 1024 + 256 + (size_t)bn * 4 + 64 + TC2_STAGE_BYTES;
-      int stages = (int)((227 * 1024 - w_region - misc - 1024) / a_stage);
       if (stages > tc2_stage_cap()) stages = tc2_stage_cap();
       if (stages >= 2) {
         Tc2Sched sc;

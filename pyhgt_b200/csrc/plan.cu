@@ -174,7 +174,8 @@ __global__ void k_tile_emit_counts(const int32_t* __restrict__ row_ptr, int64_t 
 
 __global__ void k_tile_write(const int32_t* __restrict__ row_ptr, int64_t N, int tc, int split,
                              const int64_t* __restrict__ packed_scan, int32_t* __restrict__ tiles,
-                             int64_t max_tiles, int32_t* __restrict__ n_tiles) {
+                             int64_t max_tiles, int32_t* __restrict__ n_tiles, int32_t* __restrict__ hubs,
+                             int64_t max_hubs) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k > N) return;
   int64_t slot = packed_scan[k] >> 32, pslot = packed_scan[k] & 0xffffffffll;
@@ -183,6 +184,11 @@ __global__ void k_tile_write(const int32_t* __restrict__ row_ptr, int64_t N, int
   if (deg > split) {
     int pieces = (deg + split - 1) / split;
     int per = (deg + pieces - 1) / pieces;
+    int hidx = atomicAdd(&n_tiles[2], 1);                  // hub list order is arbitrary; each hub merges alone
+    if (hidx < max_hubs) {
+      hubs[4 * hidx + 0] = (int32_t)k; hubs[4 * hidx + 1] = (int32_t)pslot; hubs[4 * hidx + 2] = pieces;
+      hubs[4 * hidx + 3] = 0;
+    }
     for (int i = 0; i < pieces; ++i) {
       if (slot + i >= max_tiles) return;
       int32_t* t = tiles + 4 * (slot + i);
@@ -314,11 +320,13 @@ extern "C" int hgt_plan_edges_fill(const int64_t* edge_index, const int64_t* edg
 }
 
 extern "C" int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges, int32_t target_edges,
-                              int32_t split_edges, int32_t* tiles, int64_t max_tiles, int32_t* d_n_tiles,
-                              int32_t* h_n_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+                              int32_t split_edges, int32_t* tiles, int64_t max_tiles, int32_t* hubs,
+                              int64_t max_hubs, int32_t* d_n_tiles, int32_t* h_n_tiles, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(target_edges >= 1 && split_edges >= 1, "hgt_plan_tiles: bad tile parameters");
-  h_n_tiles[0] = h_n_tiles[1] = 0;
+  h_n_tiles[0] = h_n_tiles[1] = h_n_tiles[2] = 0;
+  HGT_CHECK_CUDA(cudaMemsetAsync(d_n_tiles, 0, 3 * sizeof(int32_t), st));
   if (n_nodes == 0) return 0;
   int tc = 2 * target_edges;
   PlanScratch s;
@@ -332,12 +340,14 @@ extern "C" int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n
   HGT_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int64_t*)packed, packed,
                                                (int)(n_nodes + 1), st));
   k_tile_write<<<blocks_for(n_nodes + 1), kThreads, 0, st>>>(row_ptr, n_nodes, tc, split_edges, packed, tiles,
-                                                             max_tiles, d_n_tiles);
+                                                             max_tiles, d_n_tiles, hubs, max_hubs);
   HGT_LAUNCH_CHECK();
-  HGT_CHECK_CUDA(cudaMemcpyAsync(h_n_tiles, d_n_tiles, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  HGT_CHECK_CUDA(cudaMemcpyAsync(h_n_tiles, d_n_tiles, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   HGT_CHECK_CUDA(cudaStreamSynchronize(st));
   HGT_REQUIRE(h_n_tiles[0] <= max_tiles, "hgt_plan_tiles: %d tiles exceed max_tiles=%lld", h_n_tiles[0],
               (long long)max_tiles);
+  HGT_REQUIRE(h_n_tiles[2] <= max_hubs, "hgt_plan_tiles: %d hubs exceed max_hubs=%lld", h_n_tiles[2],
+              (long long)max_hubs);
   if (h_n_tiles[0] > 0) {
     k_tile_close<<<blocks_for(h_n_tiles[0]), kThreads, 0, st>>>(row_ptr, n_nodes, tiles, d_n_tiles);
     HGT_LAUNCH_CHECK();

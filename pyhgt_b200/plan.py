@@ -53,6 +53,8 @@ class GraphPlan:
     tiles: torch.Tensor           # [n_tiles,4] int32
     n_tiles: int
     n_split: int
+    hubs: torch.Tensor = None     # [n_hubs,4] int32 {dst, first partial slot, pieces, 0}
+    n_hubs: int = 0
     pair_type_dev: torch.Tensor = None
     pair_rel_dev: torch.Tensor = None
     _layer_tables: dict = field(default_factory=dict)
@@ -201,18 +203,22 @@ def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relat
 
     max_tiles = (2 * E + N) // (2 * TILE_TARGET_EDGES) + 3 * (E // TILE_SPLIT_EDGES) + 16
     tiles = torch.empty((max_tiles, 4), **i32)
-    n_tiles_d = torch.zeros(2, **i32)
-    n_tiles_h = (ctypes.c_int32 * 2)()
+    max_hubs = E // TILE_SPLIT_EDGES + 1
+    hubs = torch.empty((max_hubs, 4), **i32)
+    n_tiles_d = torch.zeros(4, **i32)
+    n_tiles_h = (ctypes.c_int32 * 4)()
     _lib.call("hgt_plan_tiles", row_ptr.data_ptr(), N, E, TILE_TARGET_EDGES, TILE_SPLIT_EDGES, tiles.data_ptr(),
-              max_tiles, n_tiles_d.data_ptr(), n_tiles_h, ws.data_ptr(), ws.numel(), st)   # synchronises
+              max_tiles, hubs.data_ptr(), max_hubs, n_tiles_d.data_ptr(), n_tiles_h, ws.data_ptr(), ws.numel(),
+              st)   # synchronises
     if tm is not None and int(flags_d[1].item()) != 0:
         raise IndexError("edge_time contains values outside [0, %d) (RelTemporalEncoding table size)" % RTE_MAX_LEN)
-    n_tiles, n_split = int(n_tiles_h[0]), int(n_tiles_h[1])
+    n_tiles, n_split, n_hubs = int(n_tiles_h[0]), int(n_tiles_h[1]), int(n_tiles_h[2])
     return GraphPlan(n_nodes=N, n_edges=E, num_types=T, num_relations=R, has_time=tm is not None,
                      sorted_types=sorted_types, rank=rank, perm=perm, type_count=type_count, type_row0=type_row0,
                      type_row0_dev=type_row0_d, row_ptr=row_ptr, csr_eid=csr_eid, kv_row=kv_row, rte_row=rte_row,
                      pairs=pairs, pair_row0=pair_row0, kv_rows=rows, tiles=tiles[:max(n_tiles, 1)],
-                     n_tiles=n_tiles, n_split=n_split, pair_type_dev=pair_type_d, pair_rel_dev=pair_rel_d)
+                     n_tiles=n_tiles, n_split=n_split, hubs=hubs[:max(n_hubs, 1)], n_hubs=n_hubs,
+                     pair_type_dev=pair_type_d, pair_rel_dev=pair_rel_d)
 
 
 # ---- typed-linear descriptor tables (depend on the plan and on the layer's d_in / d_out) -------------
