@@ -210,12 +210,12 @@ def main_ours(args, rank, local_rank, world):
         n_dst_local, e_local = shard.n_owned, shard.n_local_edges
 
     with torch.no_grad():
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()                 # nvidia-smi needs ~0.3 s to deliver its first sample: start before warm-up
         for _ in range(max(args.warmup, 3)):
             out = step()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         HGTConv.event_sink = []
         launches0 = _lib.kernel_launches()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,7 +227,8 @@ def main_ours(args, rank, local_rank, world):
         barrier()
         launches = _lib.kernel_launches() - launches0
         ms_total = ev0.elapsed_time(ev1)
-        edge_ms = [a.elapsed_time(b) for (_, a, b) in HGTConv.event_sink]
+        edge_ms = [a.elapsed_time(b) for (n, a, b) in HGTConv.event_sink if n == "edge"]
+        lin_ms = [a.elapsed_time(b) for (n, a, b) in HGTConv.event_sink if n in ("proj_linear", "upd_linear")]
         HGTConv.event_sink = None
         clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -250,6 +251,24 @@ def main_ours(args, rank, local_rank, world):
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": edge_avg_ms,
                     "share_of_step": edge_avg_ms / ms_step if ms_step else None}
+
+        # ---- typed linears (tcgen05): FLOPs of ONE fp32-equivalent product; the kernel issues 3 bf16 products ----
+        lin_total_ms = sum(lin_ms) / max(args.steps, 1)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16_peak = float(json.load(f)["bf16_tflops"])
+        except Exception:
+            bf16_peak = 1590.0
+        roofline_linear = None
+        if world == 1 and lin_total_ms > 0:
+            rows_kv = hplan.get_plan(nt, ei, et, None, TYPES, RELS).kv_rows     # cached plan of this graph
+            flops = 2.0 * D * D * (N + 2 * rows_kv + N)
+            roofline_linear = {"kernel": "k_typed_linear_tc2 (csrc/linear_tc.cu), projection + a_linear launches",
+                               "bound": "tensor", "achieved": 3 * flops / (lin_total_ms * 1e-3) / 1e12,
+                               "peak": bf16_peak, "unit": "TFLOP/s (bf16 products issued: 3 per fp32-grade product)",
+                               "frac": 3 * flops / (lin_total_ms * 1e-3) / 1e12 / bf16_peak,
+                               "fp32_equivalent_tflops": flops / (lin_total_ms * 1e-3) / 1e12,
+                               "ms_per_step": lin_total_ms, "includes": "operand hi/lo split kernels"}
 
         # ---- end to end through the module call with host buffers (N = 1 path; sharded: owned rows) ----
         e2e = None
@@ -321,7 +340,7 @@ def main_ours(args, rank, local_rank, world):
                            "parallelism": "single GPU" if world == 1 else
                                           "dst-node sharding x%d, one NCCL all-to-all of halo source rows per step" % world,
                            "linear": "tcgen05 split-bf16 (3 products, fp32 accumulate)", "edge": "TMA bulk-copy ring"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "roofline": roofline, "roofline_linear": roofline_linear, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -129,6 +129,21 @@ class HGTConv(nn.Module):
             tab = self._ptr_tables[name] = _PointerTable()
         return tab.get(tensors, device)
 
+    @staticmethod
+    def _stage(name):
+        """Context manager recording CUDA events around a stage when HGTConv.event_sink is a list (bench.py)."""
+        class _T:
+            def __enter__(self_):
+                self_.on = HGTConv.event_sink is not None
+                if self_.on:
+                    self_.a, self_.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    self_.a.record()
+            def __exit__(self_, *exc):
+                if self_.on:
+                    self_.b.record()
+                    HGTConv.event_sink.append((name, self_.a, self_.b))
+        return _T()
+
     def _typed_linear(self, a, lda, w, bias, k, width, table, out, impl, st):
         """hgt_typed_linear with its (impl-dependent) workspace; table = (groups_dev, groups_host, n, cblocks_dev)."""
         g_dev, g_host, n_g, c_dev = table
@@ -204,7 +219,8 @@ class HGTConv(nn.Module):
         q_tab = proj[lt.q_off:lt.q_off + N * d]
         kv_tab = proj[lt.kv_off:]
         kv_tab[plan.kv_rows * 2 * d:].zero_()
-        self._typed_linear(x_sorted, d_in, w_cat, b_cat, d_in, d, lt.proj_groups, proj, self.linear_impl, st)
+        with self._stage("proj_linear"):
+            self._typed_linear(x_sorted, d_in, w_cat, b_cat, d_in, d, lt.proj_groups, proj, self.linear_impl, st)
         kvr = None
         if self.use_RTE:
             # RT = lin(emb.weight) [240,d] (conv.py:299), then projected with every pair's K'/V' weights (no bias)
@@ -246,7 +262,8 @@ class HGTConv(nn.Module):
         ba = self._ptrs("ba", [l.bias for l in self.a_linears], dev)
         _lib.call("hgt_concat_linears", wa.data_ptr(), ba.data_ptr(), T, d, d, wa_cat.data_ptr(), ba_cat.data_ptr(), st)
         o = torch.empty((N, d), **f32)
-        self._typed_linear(g_act, d, wa_cat, ba_cat, d, d, lt.upd_groups, o, self.linear_impl, st)
+        with self._stage("upd_linear"):
+            self._typed_linear(g_act, d, wa_cat, ba_cat, d, d, lt.upd_groups, o, self.linear_impl, st)
         if self.training and self.drop.p > 0:
             o = self.drop(o)                                       # conv.py:125 (train mode only)
         norm_w = norm_b = None

@@ -368,3 +368,19 @@ def test_backward_hub_split_and_unsorted_types():
         scale = max(exp.abs().max().item(), 1e-6)
         assert torch.allclose(got, exp, rtol=2e-3, atol=2e-3 * scale), \
             "%s: max abs err %.3g (scale %.3g)" % (what, (got - exp).abs().max().item(), scale)
+
+
+def test_gnn_stack_matches_reference_model_golden():
+    """pyhgt_b200.model.GNN (adapter + 2 HGT layers, one shared plan) against the reference's model.py output."""
+    from pyhgt_b200.model import GNN
+    dev = _dev()
+    fx = load_golden("gnn_2layer")
+    c = fx["cfg"]
+    m = GNN(c["in_dim"], c["n_hid"], c["num_types"], c["num_relations"], c["n_heads"], c["n_layers"], 0.2, "hgt",
+            c["prev_norm"], c["last_norm"], c["use_RTE"])
+    m.load_state_dict(fx["state_dict"], strict=True)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(fx["node_feature"].to(dev), fx["node_type"].to(dev), fx["edge_time"].to(dev),
+                fx["edge_index"].to(dev), fx["edge_type"].to(dev))
+    _close(out, fx["out"], "GNN 2-layer out")

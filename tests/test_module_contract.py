@@ -60,3 +60,13 @@ def test_general_conv_dispatch():
     assert isinstance(g.base_conv, pyhgt_b200.HGTConv) and g.base_conv.use_RTE is False
     with pytest.raises(NotImplementedError):
         pyhgt_b200.GeneralConv('gcn', 32, 32, 2, 3, 4, 0.2)
+
+
+def test_gnn_wrapper_state_dict_matches_reference_fixture():
+    from pyhgt_b200.model import GNN
+    fx = load_golden("gnn_2layer")
+    c = fx["cfg"]
+    m = GNN(c["in_dim"], c["n_hid"], c["num_types"], c["num_relations"], c["n_heads"], c["n_layers"], 0.2, "hgt",
+            c["prev_norm"], c["last_norm"], c["use_RTE"])
+    assert list(m.state_dict().keys()) == list(fx["state_dict"].keys())
+    m.load_state_dict(fx["state_dict"], strict=True)
