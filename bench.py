@@ -202,7 +202,8 @@ def main_ours(args, rank, local_rank, world):
         h2d = d2h = 0
     else:
         from pyhgt_b200 import sharded
-        shard = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, None, TYPES, RELS, rank, world, dev)
+        shard = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, None, TYPES, RELS, rank, world, dev,
+                                           halo_mode=args.halo)
         x_own = x_host[shard.owned_global].to(dev)
 
         def step():
@@ -229,6 +230,9 @@ def main_ours(args, rank, local_rank, world):
         ms_total = ev0.elapsed_time(ev1)
         edge_ms = [a.elapsed_time(b) for (n, a, b) in HGTConv.event_sink if n == "edge"]
         lin_ms = [a.elapsed_time(b) for (n, a, b) in HGTConv.event_sink if n in ("proj_linear", "upd_linear")]
+        stages = {}
+        for (n, a, b) in HGTConv.event_sink:
+            stages[n] = stages.get(n, 0.0) + a.elapsed_time(b) / args.steps
         HGTConv.event_sink = None
         clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -338,9 +342,12 @@ def main_ours(args, rank, local_rank, world):
                            "plan": "destination-sorted CSR built once before the timed region (value); rebuilt every "
                                    "step in e2e",
                            "parallelism": "single GPU" if world == 1 else
-                                          "dst-node sharding x%d, one NCCL all-to-all of halo source rows per step" % world,
+                                          "dst-node sharding x%d, halo source rows per step via %s" % (
+                                              world, "one NCCL all_to_all_single" if (args.halo or os.environ.get("HGT_HALO", "nccl")) == "nccl"
+                                              else "fused NVLink peer-memory pull kernel (symmetric memory)"),
                            "linear": "tcgen05 split-bf16 (3 products, fp32 accumulate)", "edge": "TMA bulk-copy ring"},
-                "roofline": roofline, "roofline_linear": roofline_linear, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "roofline": roofline, "roofline_linear": roofline_linear,
+                "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()}, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -354,6 +361,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="graph scale (1.0 = BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default=None, choices=["nccl", "p2p"],
+                    help="multi-GPU halo exchange: one NCCL all_to_all (default) or the fused peer-memory pull kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -96,6 +96,13 @@ int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges,
 int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_rows, int32_t width,
                     float* out, void* stream);
 
+/* Multi-GPU halo exchange fused into one kernel: out[i,:] = peer[src_rank[i]][src_row[i],:], where
+ * peer_ptrs_dev is the DEVICE address of an array of world_size device pointers to every rank's [rows,width]
+ * feature buffer (NVLink peer mappings, e.g. torch symmetric memory `buffer_ptrs_dev`).  The caller orders the
+ * ranks (publish -> barrier -> pull -> barrier).  width % 4 == 0. */
+int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
+                  int32_t width, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Typed (per-node-type) linear layers — "per-type linear dispatch" (conv.py:73-77,96-97,103,125).
  * ---------------------------------------------------------------------------------------------- */

@@ -196,8 +196,9 @@ class HGTConv(nn.Module):
         if plan.sorted_types:
             x_sorted = x
         else:
-            x_sorted = torch.empty_like(x)
-            _lib.call("hgt_gather_rows", x.data_ptr(), plan.perm.data_ptr(), N, d_in, x_sorted.data_ptr(), st)
+            with self._stage("gather_rows"):
+                x_sorted = torch.empty_like(x)
+                _lib.call("hgt_gather_rows", x.data_ptr(), plan.perm.data_ptr(), N, d_in, x_sorted.data_ptr(), st)
 
         # 1. fold relation matrices into the typed K/V weights
         w_cat = torch.empty((max(lt.cat_rows, 1), d_in), **f32)
@@ -271,10 +272,13 @@ class HGTConv(nn.Module):
             norm_w = torch.stack([n.weight for n in self.norms]).contiguous()
             norm_b = torch.stack([n.bias for n in self.norms]).contiguous()
         out = torch.empty((N, d), **f32)
+        ev_e = self._stage("update_epilogue")
+        ev_e.__enter__()
         _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
                   self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
                   None if plan.sorted_types else plan.perm.data_ptr(), _lib.ptr(lt.type_active_dev), N, d,
                   out.data_ptr(), st)
+        ev_e.__exit__()
         saved = None
         if save:
             saved = dict(plan=plan, lt=lt, x_sorted=x_sorted, w_cat=w_cat, proj=proj, kvr=kvr, agg=agg, o=o,

@@ -233,6 +233,25 @@ __global__ void k_gather_rows_scalar(const float* __restrict__ in, const int32_t
   out[i] = in[(int64_t)perm[r] * width + c];
 }
 
+// Fused halo exchange: one warp per destination row pulls it from the owner's HBM (NVLink peer mapping).
+__global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
+                            const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row,
+                            float4* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const float4* src = reinterpret_cast<const float4*>(peers[src_rank[r]]) + (int64_t)src_row[r] * vec_per_row;
+    float4* dst = out + r * vec_per_row;
+    for (int c = lane; c < vec_per_row; c += 32) {
+      float4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + c));
+      dst[c] = v;
+    }
+  }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -365,6 +384,22 @@ extern "C" int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_r
   } else {
     k_gather_rows_scalar<<<blocks_for(n_rows * width), kThreads, 0, st>>>(in, perm, n_rows, width, out);
   }
+  HGT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
+                             int32_t width, float* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(width % 4 == 0, "hgt_halo_pull: row width %d must be a multiple of 4 floats", width);
+  if (n_rows == 0) return 0;
+  const int warps_per_block = 8;
+  int64_t blocks = (n_rows + warps_per_block - 1) / warps_per_block;
+  int64_t cap = (int64_t)hgt_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  k_halo_pull<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(reinterpret_cast<const float* const*>(peer_ptrs_dev),
+                                                                 src_rank, src_row, n_rows, width / 4,
+                                                                 reinterpret_cast<float4*>(out));
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -46,42 +46,63 @@ class ShardedGraph:
     n_owned: int
     n_halo: int
     n_local_edges: int
-    owned_global: torch.Tensor        # [n_owned] global ids (CPU)
-    halo_global: torch.Tensor         # [n_halo] global ids (CPU)
-    node_type: torch.Tensor           # [n_owned + n_halo] local node types (device)
+    owned_global: torch.Tensor        # [n_owned] global ids, type-sorted (CPU)
+    halo_global: torch.Tensor         # [n_halo] global ids in all-to-all arrival order: by owner, then id (CPU)
+    local_global: torch.Tensor        # [n_local] global id of every local row (CPU); local order = per type [owned | halo]
+    node_type: torch.Tensor           # [n_local] local node types, non-decreasing (device)
     edge_index: torch.Tensor          # [2, E_local] local ids (device)
     edge_type: torch.Tensor
     edge_time: torch.Tensor
-    send_idx: torch.Tensor            # [n_send] local owned positions to send, grouped by destination rank
+    send_idx: torch.Tensor            # [n_send] rows of x_own to send, grouped by destination rank
     send_splits: list
     recv_splits: list
+    cat_index: torch.Tensor           # [n_local] int32: row of concat([x_own, recv]) for every local row
+    pull_rank: torch.Tensor           # [n_local] int32: owner of every local row (P2P pull path)
+    pull_row: torch.Tensor            # [n_local] int32: row inside the owner's x_own
+    own_rows: torch.Tensor            # [n_owned] int64: local row of every owned node, in owned_global order
     active_per_type: list             # owned nodes of each type (type T = out-of-range bucket)
+    max_owned: int                    # max n_owned over ranks (symmetric buffer rows)
     num_types: int
     num_relations: int
     group: object = None
+    halo_mode: str = "nccl"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer memory
+    _symm: object = None
 
     @staticmethod
     def build(node_type, edge_index, edge_type, edge_time, num_types, num_relations, rank, world, device,
-              group=None):
+              group=None, halo_mode=None):
+        import os
         node_type, edge_index, edge_type = node_type.cpu(), edge_index.cpu(), edge_type.cpu()
         edge_time = None if edge_time is None else edge_time.cpu()
         n = node_type.numel()
         owner = partition_owner(node_type, edge_index, num_types, world)
         tkey = torch.where((node_type >= 0) & (node_type < num_types), node_type, torch.full_like(node_type, num_types))
-        mine = (owner == rank).nonzero(as_tuple=True)[0]
-        owned = mine[torch.argsort(tkey[mine], stable=True)]                 # type-sorted owned ids
+        # position of every node inside its owner's (type-sorted) owned list — identical on every rank
+        owned_pos = torch.empty(n, dtype=torch.int64)
+        max_owned = 0
+        owned = None
+        for r in range(world):
+            mine_r = (owner == r).nonzero(as_tuple=True)[0]
+            owned_r = mine_r[torch.argsort(tkey[mine_r], stable=True)]
+            owned_pos[owned_r] = torch.arange(owned_r.numel())
+            max_owned = max(max_owned, int(owned_r.numel()))
+            if r == rank:
+                owned = owned_r
         e_sel = (owner[edge_index[1]] == rank).nonzero(as_tuple=True)[0]    # in-edges of owned destinations
         src, dst = edge_index[0, e_sel], edge_index[1, e_sel]
         srcs = torch.unique(src)
         halo = srcs[owner[srcs] != rank]
-        halo = halo[torch.argsort(owner[halo] * n + halo)]                   # by owner, then id
+        halo = halo[torch.argsort(owner[halo] * n + halo)]                   # arrival order: by owner, then id
+        n_owned, n_halo = int(owned.numel()), int(halo.numel())
+        # local order: per type [owned | halo]  => node_type is sorted, Q/update act on a prefix of every type
+        cat_ids = torch.cat([owned, halo])                                   # order of concat([x_own, recv])
+        is_halo = torch.cat([torch.zeros(n_owned, dtype=torch.int64), torch.ones(n_halo, dtype=torch.int64)])
+        order = torch.argsort(tkey[cat_ids] * 2 + is_halo, stable=True)
+        local_global = cat_ids[order]
         local_of = torch.full((n,), -1, dtype=torch.int64)
-        local_of[owned] = torch.arange(owned.numel())
-        local_of[halo] = owned.numel() + torch.arange(halo.numel())
+        local_of[local_global] = torch.arange(local_global.numel())
         ei_local = torch.stack([local_of[src], local_of[dst]])
-        nt_local = torch.cat([node_type[owned], node_type[halo]])
         recv_splits = torch.bincount(owner[halo], minlength=world).tolist()
-        # what every peer asks of me: replay the same deterministic construction for each destination rank
         send_lists = []
         dst_owner_all = owner[edge_index[1]]
         src_owner_all = owner[edge_index[0]]
@@ -90,43 +111,81 @@ class ShardedGraph:
                 send_lists.append(torch.zeros(0, dtype=torch.int64))
                 continue
             need = (dst_owner_all == p) & (src_owner_all == rank)
-            ids = torch.unique(edge_index[0, need.nonzero(as_tuple=True)[0]])   # ascending = the peer's halo order
-            send_lists.append(local_of[ids])
-        send_splits = [int(s.numel()) for s in send_lists]
+            ids = torch.unique(edge_index[0, need.nonzero(as_tuple=True)[0]])   # ascending = the peer's arrival order
+            send_lists.append(owned_pos[ids])
+        send_splits = [int(x.numel()) for x in send_lists]
         send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, dtype=torch.int64)
         active = torch.bincount(tkey[owned], minlength=num_types + 1).tolist()
-        return ShardedGraph(rank=rank, world=world, device=device, n_owned=int(owned.numel()),
-                            n_halo=int(halo.numel()), n_local_edges=int(e_sel.numel()), owned_global=owned,
-                            halo_global=halo, node_type=nt_local.to(device), edge_index=ei_local.to(device),
-                            edge_type=edge_type[e_sel].to(device),
+        mode = halo_mode or os.environ.get("HGT_HALO", "nccl")
+        return ShardedGraph(rank=rank, world=world, device=device, n_owned=n_owned, n_halo=n_halo,
+                            n_local_edges=int(e_sel.numel()), owned_global=owned, halo_global=halo,
+                            local_global=local_global, node_type=node_type[local_global].to(device),
+                            edge_index=ei_local.to(device), edge_type=edge_type[e_sel].to(device),
                             edge_time=None if edge_time is None else edge_time[e_sel].to(device),
                             send_idx=send_idx.to(device), send_splits=send_splits, recv_splits=recv_splits,
-                            active_per_type=active, num_types=num_types, num_relations=num_relations, group=group)
+                            cat_index=order.to(torch.int32).to(device),
+                            pull_rank=owner[local_global].to(torch.int32).to(device),
+                            pull_row=owned_pos[local_global].to(torch.int32).to(device),
+                            own_rows=local_of[owned].to(device), active_per_type=active, max_owned=max_owned,
+                            num_types=num_types, num_relations=num_relations, group=group, halo_mode=mode)
 
     # --------------------------------------------------------------------------------------------
-    def exchange(self, x_own):
-        """[n_owned, d] owned rows -> [n_owned + n_halo, d] local rows (owned first), one all-to-all."""
-        d = x_own.shape[1]
-        x_local = torch.empty((self.n_owned + self.n_halo, d), dtype=x_own.dtype, device=x_own.device)
-        x_local[:self.n_owned].copy_(x_own)
-        if x_own.is_cuda and self.send_idx.numel() > 0:
+    def _gather(self, src, idx32, n_rows):
+        d = src.shape[1]
+        if src.is_cuda:
             from . import _lib
-            send = torch.empty((self.send_idx.numel(), d), dtype=x_own.dtype, device=x_own.device)
-            if getattr(self, "_send_idx32", None) is None:
-                self._send_idx32 = self.send_idx.to(torch.int32)
-            _lib.call("hgt_gather_rows", x_own.contiguous().data_ptr(), self._send_idx32.data_ptr(),
-                      self.send_idx.numel(), d, send.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        else:
-            send = x_own.index_select(0, self.send_idx)
-        recv = x_local[self.n_owned:]
+            out = torch.empty((n_rows, d), dtype=src.dtype, device=src.device)
+            if n_rows:
+                _lib.call("hgt_gather_rows", src.contiguous().data_ptr(), idx32.data_ptr(), n_rows, d, out.data_ptr(),
+                          torch.cuda.current_stream().cuda_stream)
+            return out
+        return src.index_select(0, idx32.long())
+
+    def exchange(self, x_own):
+        """[n_owned, d] owned rows -> [n_local, d] local rows in local (type-sorted) order."""
+        if self.halo_mode == "p2p" and x_own.is_cuda and self.world > 1:
+            return self._exchange_p2p(x_own)
+        d = x_own.shape[1]
+        if getattr(self, "_send_idx32", None) is None:
+            self._send_idx32 = self.send_idx.to(torch.int32)
+        buf = torch.empty((self.n_owned + self.n_halo, d), dtype=x_own.dtype, device=x_own.device)
+        buf[:self.n_owned].copy_(x_own)
+        send = self._gather(x_own, self._send_idx32, self.send_idx.numel())
         if self.world > 1:
-            dist.all_to_all_single(recv, send, self.recv_splits, self.send_splits, group=self.group)
+            dist.all_to_all_single(buf[self.n_owned:], send, self.recv_splits, self.send_splits, group=self.group)
+        return self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
+
+    def _exchange_p2p(self, x_own):
+        """Fused halo exchange: every rank publishes x_own in NVLink-mapped symmetric memory and ONE kernel pulls
+        each local row (owned and halo alike) straight from its owner's HBM into type-sorted position — no send-side
+        gather, no NCCL call, no re-ordering pass."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        d = x_own.shape[1]
+        if self._symm is None or self._symm[0].shape[1] != d:
+            buf = symm_mem.empty((max(self.max_owned, 1), d), dtype=torch.float32, device=x_own.device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            self._symm = (buf, hdl)
+        buf, hdl = self._symm
+        hdl.barrier(channel=0)                       # peers finished reading the previous layer's rows
+        buf[:self.n_owned].copy_(x_own)
+        hdl.barrier(channel=1)                       # every rank's rows are published
+        n_local = self.n_owned + self.n_halo
+        x_local = torch.empty((n_local, d), dtype=torch.float32, device=x_own.device)
+        _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
+                  x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return x_local
 
-    def forward(self, conv, x_own, edge_time_used=True):
+    def forward(self, conv, x_own):
         """One HGTConv layer on this rank's shard; returns the [n_owned, d] output rows (owned_global order)."""
-        x_local = self.exchange(x_own)
+        from .conv import HGTConv
+        with HGTConv._stage("halo_exchange"):
+            x_local = self.exchange(x_own)
         out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
                                          self.edge_time if conv.use_RTE else None, want_att=False, save=False,
                                          active_per_type=self.active_per_type)
-        return out[:self.n_owned]
+        with HGTConv._stage("collect_owned"):
+            if getattr(self, "_own_rows32", None) is None:
+                self._own_rows32 = self.own_rows.to(torch.int32)
+            res = self._gather(out, self._own_rows32, self.n_owned)
+        return res

@@ -37,10 +37,10 @@ def _worker(rank, world, port, ret):
                                         torch.device("cpu"))
         x_local = sh.exchange(x[sh.owned_global])
         # the exchange delivered exactly the halo rows
-        assert torch.equal(x_local[sh.n_owned:], x[sh.halo_global])
+        assert torch.equal(x_local, x[sh.local_global])
         loc, _ = hgt_oracle.hgt_forward_ref_port(params, x_local, sh.node_type, sh.edge_index, sh.edge_type,
                                                  sh.edge_time, **kw)
-        err = (loc[:sh.n_owned] - full[sh.owned_global]).abs().max().item()
+        err = (loc[sh.own_rows] - full[sh.owned_global]).abs().max().item()
         owned = torch.zeros(g.num_nodes, dtype=torch.int64)
         owned[sh.owned_global] = 1
         dist.all_reduce(owned)
