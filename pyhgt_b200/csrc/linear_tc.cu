@@ -501,6 +501,291 @@ k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
+
+// ---- 2-CTA (cta_group::2) W-stationary persistent GEMM -------------------------------------------
+// A CTA pair (cluster of 2, same TPC) computes a 256 x 256 tile per step: each CTA owns 128 rows of A / of the
+// accumulator and keeps HALF of the column task's W (128 of the 256 columns, all K, hi + lo) resident; the
+// tcgen05.mma.cta_group::2 instruction issued by the leader reads both halves of W from the two CTAs' shared
+// memory.  Each A byte streamed from L2 now feeds a 256-column product, so the A stream needs half the
+// bandwidth / in-flight bytes of the single-CTA kernel above (which it could not sustain: TMA-latency-bound at
+// ~45 % tensor-pipe utilisation).
+// Barrier protocol: a_full / w_full live in the LEADER (both CTAs' TMA loads complete_tx there through the
+// peer-bit-masked address, the leader's producer posts expect_tx for both); a_empty / w_empty / t_full are
+// per-CTA and signalled by multicast tcgen05.commit; t_empty lives in the leader and collects the 8 epilogue
+// warps of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  // acquire at cluster scope: the barrier may have been completed by the peer CTA's arrivals
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   const float* __restrict__ bias, int Kp, int cb_width, int stages,
+                   const hgt_lin_group* __restrict__ groups, int n_groups,
+                   const hgt_lin_cblock* __restrict__ cblocks, float* __restrict__ out, Tc2Sched sc, int MCH) {
+  constexpr int BNH = 128;              // W columns resident per CTA
+  constexpr int BNP = 256;              // columns per pair step
+  constexpr int BMP = 256;              // rows per pair step
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);
+  const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;
+  const uint32_t b_bytes = (uint32_t)BNH * TC_BK * 2;               // 16 KB
+  const uint32_t w_region = (uint32_t)k_blocks * 2 * b_bytes;
+  unsigned char* w_smem = smem;
+  unsigned char* a_smem = smem + w_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)stages * a_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + stages;
+  uint64_t* w_full = bars + 2 * stages;
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* t_full = w_empty + 1;       // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_stage = s_bias + BNP;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int total_units = sc.first_unit[n_groups];
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(s_u32(&a_full[s]), 1);
+      mbar_init(s_u32(&a_empty[s]), 1);
+    }
+    mbar_init(s_u32(w_full), 1);
+    mbar_init(s_u32(w_empty), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_u32(&t_full[b]), 1);
+      mbar_init(s_u32(&t_empty[b]), 8);                              // 4 epilogue warps x 2 CTAs (used in the leader)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                                                // both CTAs' barriers exist before any remote arrive
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  struct Unit { int64_t pm_first; int n_pm; int a_row0; int w_row; int64_t m_rows; int64_t out_off; int64_t ld; int n0;
+                int has_bias; };
+  auto decode = [&](int u, Unit& un) {
+    int g = 0;
+    while (g + 1 < n_groups && u >= sc.first_unit[g + 1]) ++g;
+    const hgt_lin_group grp = groups[g];
+    int local = u - sc.first_unit[g];
+    const int ncol = grp.n_cblocks * sc.n_tiles_n;
+    const int chunk = local / ncol;
+    const int col = local - chunk * ncol;
+    const int cb = col / sc.n_tiles_n;
+    const int nt = col - cb * sc.n_tiles_n;
+    const hgt_lin_cblock cblk = cblocks[grp.cb_first + cb];
+    const int64_t pm_total = (grp.m + BMP - 1) / BMP;
+    un.pm_first = (int64_t)chunk * MCH;
+    un.n_pm = (int)min((int64_t)MCH, pm_total - un.pm_first);
+    un.a_row0 = (int)grp.a_row0;
+    un.m_rows = grp.m;
+    un.n0 = nt * BNP;
+    un.w_row = grp.w_row0 + cb * cb_width + un.n0;
+    un.out_off = cblk.out_off;
+    un.ld = cblk.ld;
+    un.has_bias = grp.has_bias;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      uint32_t a_it = 0, unit_it = 0;
+      for (int u = pair_id; u < total_units; u += n_pairs, ++unit_it) {
+        Unit un;
+        decode(u, un);
+        mbar_wait_cluster(s_u32(w_empty), (unit_it & 1u) ^ 1u);
+        if (leader) mbar_expect_tx(s_u32(w_full), 2u * (uint32_t)k_blocks * 2 * b_bytes);
+        const int w_row = un.w_row + (int)cta * BNH;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tma_load_2d_2sm(s_u32(w_smem + (size_t)(2 * kb) * b_bytes), &map_w_hi, kb * TC_BK, w_row, s_u32(w_full));
+          tma_load_2d_2sm(s_u32(w_smem + (size_t)(2 * kb + 1) * b_bytes), &map_w_lo, kb * TC_BK, w_row, s_u32(w_full));
+        }
+        for (int pm = 0; pm < un.n_pm; ++pm) {
+          const int a_row = un.a_row0 + (int)((un.pm_first + pm) * BMP) + (int)cta * TC_BM;
+          for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
+            const int s = a_it % stages;
+            mbar_wait_cluster(s_u32(&a_empty[s]), ((a_it / stages) & 1u) ^ 1u);
+            const uint32_t bar = s_u32(&a_full[s]);
+            if (leader) mbar_expect_tx(bar, 2u * a_bytes);
+            tma_load_2d_2sm(s_u32(a_smem + (size_t)s * a_bytes), (j & 1) ? &map_a_lo : &map_a_hi, (j >> 1) * TC_BK,
+                            a_row, bar);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNP >> 3) << 17) |
+                             ((uint32_t)(BMP >> 4) << 24);
+      uint32_t a_it = 0, unit_it = 0, acc_it = 0;
+      for (int u = pair_id; u < total_units; u += n_pairs, ++unit_it) {
+        Unit un;
+        decode(u, un);
+        mbar_wait_cluster(s_u32(w_full), unit_it & 1u);
+        for (int pm = 0; pm < un.n_pm; ++pm, ++acc_it) {
+          const uint32_t buf = acc_it & 1u;
+          mbar_wait_cluster(s_u32(&t_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + buf * (uint32_t)BNP;
+          for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
+            const int s = a_it % stages;
+            const int kb = j >> 1;
+            mbar_wait_cluster(s_u32(&a_full[s]), (a_it / stages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t d_a = make_sw128_desc(s_u32(a_smem + (size_t)s * a_bytes));
+            const uint64_t d_whi = make_sw128_desc(s_u32(w_smem + (size_t)(2 * kb) * b_bytes));
+            if (!(j & 1)) {
+              const uint64_t d_wlo = make_sw128_desc(s_u32(w_smem + (size_t)(2 * kb + 1) * b_bytes));
+#pragma unroll
+              for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                umma_bf16_ss_2sm(tmem_d, d_a + o, d_whi + o, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_ss_2sm(tmem_d, d_a + o, d_wlo + o, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                umma_bf16_ss_2sm(tmem_d, d_a + o, d_whi + o, idesc, 1u);
+              }
+            }
+            umma_commit_2sm(s_u32(&a_empty[s]));
+          }
+          umma_commit_2sm(s_u32(&t_full[buf]));
+        }
+        umma_commit_2sm(s_u32(w_empty));
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns =====
+    const int lg = warp & 3;
+    const int et = threadIdx.x - 64;
+    uint32_t acc_it = 0;
+    float* stg = s_stage + (size_t)lg * (32 * TC2_STG_LD);
+    const int sub = lane & 3, rsel = lane >> 2;
+    for (int u = pair_id; u < total_units; u += n_pairs) {
+      Unit un;
+      decode(u, un);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = et; c < BNP; c += 128) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int pm = 0; pm < un.n_pm; ++pm, ++acc_it) {
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait_cluster(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t m0 = (un.pm_first + pm) * BMP + (int64_t)cta * TC_BM;
+        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP;
+        for (int c0 = 0; c0 < BNP; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_row + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * TC2_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = 8 * k + rsel;
+            if (m0 + lg * 32 + rr < un.m_rows) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * TC2_STG_LD + sub * 4);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              *reinterpret_cast<float4*>(out + un.out_off + (m0 + lg * 32 + rr) * un.ld + un.n0 + c0 + sub * 4) = v;
+            }
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(s_u32(&t_empty[buf]), 0);      // the leader's barrier collects both CTAs
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                                // peer may still be reading our W through the MMA
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -552,6 +837,7 @@ void extents(const hgt_lin_group* h_groups, int n_groups, int cb_width, int64_t*
 
 }  // namespace
 
+static const bool g_tc_no_pair = [] { const char* e = getenv("HGT_TC_NO_PAIR"); return e && e[0] == '1'; }();
 static const bool g_tc_tile_per_cta = [] { const char* e = getenv("HGT_TC_TILE_PER_CTA"); return e && e[0] == '1'; }();
 
 bool hgt_typed_linear_tc_supported(int64_t lda, int32_t K, int32_t cb_width) {
@@ -599,6 +885,39 @@ int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float
   if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, BN))) return rc;
 
   const int k_blocks = (Kp + TC_BK - 1) / TC_BK;
+  if (!g_tc_tile_per_cta && !g_tc_no_pair && cb_width % 256 == 0) {
+    // ---- 2-CTA kernel: 128 W columns resident per CTA, pair tile 256 x 256 ----
+    const size_t w_region = (size_t)k_blocks * 2 * 128 * TC_BK * 2;
+    const size_t a_stage = (size_t)TC_BM * TC_BK * 2;
+    const size_t misc = 1024 + 256 + 256 * 4 + 64 + TC2_STAGE_BYTES + 1024;
+    if (w_region + misc + 4 * a_stage <= 227 * 1024) {
+      int stages = (int)((227 * 1024 - w_region - misc) / a_stage);
+      if (stages > tc2_stage_cap()) stages = tc2_stage_cap();
+      Tc2Sched sc;
+      const int mch = tc2_mch();
+      sc.n_tiles_n = cb_width / 256;
+      int64_t units = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        sc.first_unit[g] = (int32_t)units;
+        int64_t pm = (h_groups[g].m + 255) / 256;
+        units += (pm + mch - 1) / mch * h_groups[g].n_cblocks * sc.n_tiles_n;
+        HGT_REQUIRE(units < 2147483647ll, "hgt_typed_linear(tc): too many units");
+      }
+      sc.first_unit[n_groups] = (int32_t)units;
+      if (units == 0) return 0;
+      if ((rc = make_map(&m_w_hi, w_hi, w_rows, Kp, 128))) return rc;
+      if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, 128))) return rc;
+      size_t smem = 1024 + w_region + (size_t)stages * a_stage + (2 * stages + 6) * 8 + 16 + 256 * 4 + 64 +
+                    TC2_STAGE_BYTES;
+      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_typed_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int pairs = hgt_sm_count() / 2;
+      if (pairs > units) pairs = (int)units;
+      k_typed_linear_tc3<<<2 * pairs, TC2_THREADS, smem, st>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, bias, Kp, cb_width,
+                                                               stages, groups, n_groups, cblocks, out, sc, mch);
+      HGT_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (!g_tc_tile_per_cta) {
     // ---- W-stationary persistent kernel ----
     // widest n-tile whose resident W (all K, hi + lo) still leaves room for >= 4 A stages of 16 KB
