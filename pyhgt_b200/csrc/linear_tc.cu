@@ -279,9 +279,44 @@ k_typed_linear_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 // below) to 128 KB (+ W amortised over the chunk).
 static int tc2_mch() { static int v = [] { const char* e = getenv("HGT_TC_MCH"); int x = e ? atoi(e) : 8; return x < 1 ? 1 : x; }(); return v; }
 static int tc2_stage_cap() { static int v = [] { const char* e = getenv("HGT_TC_STAGES"); int x = e ? atoi(e) : 8; return x < 2 ? 2 : x; }(); return v; }
-constexpr int TC2_THREADS = 192;
+
+// Epilogue of one accumulator tile, shared by the persistent kernels.  8 epilogue warps: warp e (0..7) reads TMEM
+// lane quarter (warp id % 4) and the 16-column chunks c0 = 16*(e/4), +32, ...  TMEM hands each lane one ROW, so the
+// chunk is transposed through a per-warp staging buffer and written with 4 lanes per 64 contiguous bytes of a row
+// (full 32-byte sectors).  All shared-memory reads are issued before the dependent adds / predicated stores.
+constexpr int TC2_EPI_WARPS = 8;
+constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
 constexpr int TC2_STG_LD = 20;                 // floats per staged row (16 + 4 pad)
-constexpr int TC2_STAGE_BYTES = 4 * 32 * TC2_STG_LD * 4;
+constexpr int TC2_STAGE_BYTES = TC2_EPI_WARPS * 32 * TC2_STG_LD * 4;
+
+__device__ __forceinline__ void tc_epilogue_tile(uint32_t t_row, int n_cols, int chunk0, float* stg, const float* s_bias,
+                                                 float* out_tile, int64_t ld, int64_t rows_left, int lane) {
+  // out_tile: address of (first row of this warp's 32-row slab, column 0 of the tile); rows_left: valid rows in the slab
+  const int sub = lane & 3, rsel = lane >> 2;
+  for (int c0 = 16 * chunk0; c0 < n_cols; c0 += 32) {
+    uint32_t r[16];
+    tmem_ld16(t_row + (uint32_t)c0, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<uint4*>(stg + lane * TC2_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    __syncwarp();
+    const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(stg + (8 * k + rsel) * TC2_STG_LD + sub * 4);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rr = 8 * k + rsel;
+      if (rr < rows_left) {
+        float4 w = v[k];
+        w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+        *reinterpret_cast<float4*>(out_tile + (int64_t)rr * ld + c0 + sub * 4) = w;
+      }
+    }
+  }
+}
 
 struct Tc2Sched {
   int32_t first_unit[kMaxGroups + 1];
@@ -332,7 +367,7 @@ k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     mbar_init(s_u32(w_empty), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_u32(&t_full[b]), 1);
-      mbar_init(s_u32(&t_empty[b]), 4);                              // one arrival per epilogue warp
+      mbar_init(s_u32(&t_empty[b]), TC2_EPI_WARPS);                  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -445,48 +480,25 @@ k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
     }
   } else {
-    // ===== epilogue warps =====
+    // ===== epilogue warps (8) =====
     const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const int et = threadIdx.x - 64;                                 // 0..127 among epilogue threads
+    const int e = warp - 2;
+    const int et = threadIdx.x - 64;
+    float* stg = s_stage + (size_t)e * (32 * TC2_STG_LD);
     uint32_t acc_it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       Unit un;
       decode(u, un);
-      asm volatile("bar.sync 1, 128;" ::: "memory");               // previous unit's bias reads are finished
-      for (int c = et; c < BN; c += 128) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");               // previous unit's bias reads are finished
+      for (int c = et; c < BN; c += 32 * TC2_EPI_WARPS) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int mt = 0; mt < un.n_mt; ++mt, ++acc_it) {
         const uint32_t buf = acc_it & 1u;
         mbar_wait(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t m0 = (un.m_first + mt) * TC_BM;
-        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN;
-        // TMEM gives each lane one ROW; storing that directly would make every STG touch 32 different lines.
-        // Transpose 32x16 blocks through a per-warp staging buffer so that 4 lanes write 64 contiguous bytes of
-        // a row (8 rows, 16 full sectors per store instruction).
-        float* stg = s_stage + (size_t)lg * (32 * TC2_STG_LD);
-        const int sub = lane & 3, rsel = lane >> 2;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_row + (uint32_t)c0, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(stg + lane * TC2_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-          __syncwarp();
-          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rr = 8 * k + rsel;                            // row inside this warp's 32-row slab
-            if (m0 + lg * 32 + rr < un.m_rows) {
-              float4 v = *reinterpret_cast<const float4*>(stg + rr * TC2_STG_LD + sub * 4);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              *reinterpret_cast<float4*>(out + un.out_off + (m0 + lg * 32 + rr) * un.ld + un.n0 + c0 + sub * 4) = v;
-            }
-          }
-          __syncwarp();
-        }
+        const int64_t m0 = (un.m_first + mt) * TC_BM + lg * 32;
+        tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, stg, s_bias,
+                         out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&t_empty[buf])) : "memory");
@@ -620,7 +632,7 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     mbar_init(s_u32(w_empty), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_u32(&t_full[b]), 1);
-      mbar_init(s_u32(&t_empty[b]), 8);                              // 4 epilogue warps x 2 CTAs (used in the leader)
+      mbar_init(s_u32(&t_empty[b]), 2 * TC2_EPI_WARPS);              // epilogue warps of both CTAs (used in the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -734,44 +746,25 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
     }
   } else {
-    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns =====
+    // ===== epilogue warps (8 per CTA): own 128 rows x 256 columns =====
     const int lg = warp & 3;
+    const int e = warp - 2;
     const int et = threadIdx.x - 64;
+    float* stg = s_stage + (size_t)e * (32 * TC2_STG_LD);
     uint32_t acc_it = 0;
-    float* stg = s_stage + (size_t)lg * (32 * TC2_STG_LD);
-    const int sub = lane & 3, rsel = lane >> 2;
     for (int u = pair_id; u < total_units; u += n_pairs) {
       Unit un;
       decode(u, un);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = et; c < BNP; c += 128) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = et; c < BNP; c += 32 * TC2_EPI_WARPS) s_bias[c] = (un.has_bias && bias) ? bias[un.w_row + c] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int pm = 0; pm < un.n_pm; ++pm, ++acc_it) {
         const uint32_t buf = acc_it & 1u;
         mbar_wait_cluster(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t m0 = (un.pm_first + pm) * BMP + (int64_t)cta * TC_BM;
-        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP;
-        for (int c0 = 0; c0 < BNP; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_row + (uint32_t)c0, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(stg + lane * TC2_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-          __syncwarp();
-          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rr = 8 * k + rsel;
-            if (m0 + lg * 32 + rr < un.m_rows) {
-              float4 v = *reinterpret_cast<const float4*>(stg + rr * TC2_STG_LD + sub * 4);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              *reinterpret_cast<float4*>(out + un.out_off + (m0 + lg * 32 + rr) * un.ld + un.n0 + c0 + sub * 4) = v;
-            }
-          }
-          __syncwarp();
-        }
+        const int64_t m0 = (un.pm_first + pm) * BMP + (int64_t)cta * TC_BM + lg * 32;
+        tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, stg, s_bias,
+                         out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_cta(s_u32(&t_empty[buf]), 0);      // the leader's barrier collects both CTAs
