@@ -156,6 +156,14 @@ int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* b
                      int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
                      int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, int32_t impl,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Same product on the tensor-core kernel with the A operand already split by its producer: a_hi / a_lo are bf16
+ * [rows, K] (K % 8 == 0, row stride K).  Saves the split pass over A (workspace: W split only). */
+int hgt_typed_linear_presplit_workspace_bytes(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K,
+                                              int32_t cb_width, size_t* out_bytes);
+int hgt_typed_linear_presplit(const void* a_hi, const void* a_lo, const float* W, const float* bias, int32_t K,
+                              int32_t cb_width, const hgt_lin_group* groups, const hgt_lin_group* h_groups,
+                              int32_t n_groups, const hgt_lin_cblock* cblocks, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused edge kernel: gather -> relation-specific score -> softmax by destination -> weighted sum
@@ -169,6 +177,8 @@ int hgt_typed_linear(const float* A, int64_t lda, const float* W, const float* b
  *  agg_out [N, d]  gelu(sum_e att[e] * V'[e]) if apply_gelu else the raw sum   (conv.py:119)
  *  att_out [E, H]  softmax weights in ORIGINAL edge order (conv.py:108 `self.att`) or NULL
  *  stats_out [N, 2H] per-destination (max, sum) per head, or NULL (kept for the backward pass)
+ *  g_hi / g_lo [N, d] bf16 or NULL: the same result as a bf16 hi/lo split (x = hi + lo to ~2^-17), i.e. the
+ *           pre-split A operand of hgt_typed_linear_presplit; agg_out may then be NULL.  Needs d % 8 == 0.
  *  variant: 0 = auto, 1 = direct register gather (LDG), 2 = bulk-async-copy shared-memory ring (TMA) */
 int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_t n_heads, size_t* out_bytes);
 int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
@@ -176,7 +186,7 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      const int32_t* csr_eid, const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles,
                      const int32_t* hubs, int32_t n_hubs,
                      int64_t n_nodes, int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu,
-                     float* agg_out, float* att_out, float* stats_out,
+                     float* agg_out, float* att_out, float* stats_out, void* g_hi, void* g_lo,
                      void* workspace, size_t workspace_bytes, int32_t variant, void* stream);
 
 /* Backward of hgt_edge_forward (training; the reference differentiates the same ops with autograd,

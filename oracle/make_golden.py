@@ -65,6 +65,28 @@ def conv_case(name, graph, d, heads, use_norm, use_RTE, seed, grads=False, feat_
                                                  os.path.getsize(path) / 1024))
 
 
+def dense_case(name, graph, d, heads, use_norm, use_RTE, seed):
+    """DenseHGTConv.forward (conv.py:143-280): same message(), residual + LayerNorm + shared FFN update."""
+    conv, _ = pyg_shim.load_reference()
+    torch.manual_seed(seed)
+    m = conv.DenseHGTConv(d, d, graph.num_types, graph.num_relations, heads, 0.2, use_norm, use_RTE)
+    _perturb(m, seed + 1)
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 2)
+    x = torch.randn(graph.num_nodes, d, generator=g)
+    with torch.no_grad():
+        out = m(x, graph.node_type, graph.edge_index, graph.edge_type, graph.edge_time).clone()
+    fx = {"cfg": dict(in_dim=d, out_dim=d, num_types=graph.num_types, num_relations=graph.num_relations,
+                      n_heads=heads, use_norm=use_norm, use_RTE=use_RTE),
+          "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+          "node_inp": x, "node_type": graph.node_type, "edge_index": graph.edge_index,
+          "edge_type": graph.edge_type, "edge_time": graph.edge_time, "out": out, "att": m.att.detach().clone()}
+    path = os.path.join(OUT_DIR, name + ".pt")
+    torch.save(fx, path)
+    print("%-28s N=%d E=%d d=%d H=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, d, heads,
+                                                 os.path.getsize(path) / 1024))
+
+
 def gnn_case(name, graph, in_dim, n_hid, heads, n_layers, seed):
     """GNN.forward (model.py:69-80): per-type adapter + stack of GeneralConv('hgt')."""
     _, model = pyg_shim.load_reference()
@@ -115,6 +137,9 @@ def main():
     # whole-model fixture: reference GNN (adapter + 2 HGT layers)
     g = synth.make_random(250, 2000, 3, 3, seed=26, sorted_types=True, self_loops=250)
     gnn_case("gnn_2layer", g, 48, 64, 4, 2, seed=17)
+    # DenseHGTConv variant (unsorted types, isolated destinations), d=64 so the FFN runs on the tensor-core GEMM
+    g = synth.make_random(300, 2400, 3, 3, seed=27, isolated_frac=0.2, self_loops=30)
+    dense_case("dense_hgt", g, 64, 4, True, True, seed=18)
 
 
 if __name__ == "__main__":

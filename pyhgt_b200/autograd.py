@@ -41,7 +41,8 @@ class _EdgeAttention(torch.autograd.Function):
         _lib.call("hgt_edge_forward", q.data_ptr(), kv.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
                   plan.kv_row.data_ptr(), None if kvr is None else plan.rte_row.data_ptr(), plan.csr_eid.data_ptr(),
                   plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, plan.n_edges, d, n_heads, 0,
-                  agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), ws.data_ptr(), ws.numel(), variant, _stream())
+                  agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), variant,
+                  _stream())
         ctx.plan, ctx.n_heads, ctx.has_kvr = plan, n_heads, kvr is not None
         ctx.save_for_backward(q, kv, kvr if kvr is not None else q.new_empty(0), agg, stats)
         ctx.mark_non_differentiable(*([att] if att is not None else []))

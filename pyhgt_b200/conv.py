@@ -79,6 +79,7 @@ class HGTConv(nn.Module):
     edge_variant = 0           # 0 auto, 1 register gather, 2 bulk-copy ring (see csrc/edge.cu)
     linear_impl = 0            # 0 auto, 1 fp32 SIMT, 2 tcgen05
     event_sink = None          # bench.py: list receiving (stage, start_event, end_event) on the launch stream
+    _has_skip = True           # DenseHGTConv (conv.py:143-280) has no skip gate
 
     def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
                  use_RTE=True, **kwargs):
@@ -110,7 +111,8 @@ class HGTConv(nn.Module):
         self.relation_pri = nn.Parameter(torch.ones(num_relations, self.n_heads))
         self.relation_att = nn.Parameter(torch.Tensor(num_relations, n_heads, self.d_k, self.d_k))
         self.relation_msg = nn.Parameter(torch.Tensor(num_relations, n_heads, self.d_k, self.d_k))
-        self.skip = nn.Parameter(torch.ones(num_types))
+        if self._has_skip:
+            self.skip = nn.Parameter(torch.ones(num_types))
         self.drop = nn.Dropout(dropout)
         if self.use_RTE:
             self.emb = RelTemporalEncoding(in_dim)
@@ -182,6 +184,26 @@ class HGTConv(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
                       active_per_type=None):
+        c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
+                       gelu_before_a=True)
+        plan, lt, o, x_sorted, N, d, T, st = c["plan"], c["lt"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
+        f32 = dict(dtype=torch.float32, device=o.device)
+        norm_w = norm_b = None
+        if self.use_norm:
+            norm_w = torch.stack([n.weight for n in self.norms]).contiguous()
+            norm_b = torch.stack([n.bias for n in self.norms]).contiguous()
+        out = torch.empty((N, d), **f32)
+        with self._stage("update_epilogue"):
+            _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
+                      self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
+                      None if plan.sorted_types else plan.perm.data_ptr(), _lib.ptr(lt.type_active_dev), N, d,
+                      out.data_ptr(), st)
+        return out, c["att"], (c if save else None)
+
+    def _core(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
+              gelu_before_a):
+        """Everything up to and including the typed a_linear: plan, weight fold, typed projections, fused edge kernel
+        (gelu fused iff gelu_before_a and not save), a_linears.  Returns a dict of the intermediates."""
         dev = node_inp.device
         d_in, d = self.in_dim, self.out_dim
         H, T, R = self.n_heads, self.num_types, self.num_relations
@@ -236,27 +258,28 @@ class HGTConv(nn.Module):
         ws_bytes = ctypes.c_size_t()
         _lib.call("hgt_edge_workspace_bytes", plan.n_split, d, H, ctypes.byref(ws_bytes))
         ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
-        g_act = torch.empty((N, d), **f32)
+        # When the a_linear GEMM will run on the tensor cores, the edge kernel writes gelu(agg) directly as the bf16
+        # hi/lo operand split (no fp32 round trip, no separate split pass).
+        fuse_split = (gelu_before_a and not save and self.linear_impl in (0, 2) and d % 16 == 0 and d >= 64
+                      and not (self.training and self.drop.p > 0))
+        g_act = None if fuse_split else torch.empty((N, d), **f32)
+        g_hi = torch.empty((N, d), dtype=torch.bfloat16, device=dev) if fuse_split else None
+        g_lo = torch.empty((N, d), dtype=torch.bfloat16, device=dev) if fuse_split else None
         att = torch.empty((E, H), **f32) if want_att else None
         stats = torch.empty((N, 2 * H), **f32) if save else None
-        ev0 = ev1 = None
-        if HGTConv.event_sink is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        _lib.call("hgt_edge_forward", q_tab.data_ptr(), kv_tab.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
-                  plan.kv_row.data_ptr(), _lib.ptr(plan.rte_row) if self.use_RTE else None,
-                  plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, E, d, H,
-                  0 if save else 1, g_act.data_ptr(), _lib.ptr(att), _lib.ptr(stats), ws.data_ptr(), ws.numel(),
-                  self.edge_variant, st)
-        if ev0 is not None:
-            ev1.record()
-            HGTConv.event_sink.append(("edge", ev0, ev1))
+        with self._stage("edge"):
+            _lib.call("hgt_edge_forward", q_tab.data_ptr(), kv_tab.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
+                      plan.kv_row.data_ptr(), _lib.ptr(plan.rte_row) if self.use_RTE else None,
+                      plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split,
+                      plan.hubs.data_ptr(), plan.n_hubs, N, E, d, H, 1 if (gelu_before_a and not save) else 0,
+                      _lib.ptr(g_act), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(g_hi), _lib.ptr(g_lo), ws.data_ptr(),
+                      ws.numel(), self.edge_variant, st)
 
-        # 4. typed output linear (conv.py:125) + gated skip + LayerNorm (conv.py:129-133)
+        # 4. typed output linear (conv.py:125 / conv.py:261)
         agg = None
-        if save:
+        if save or not gelu_before_a:
             agg = g_act
-            g_act = F.gelu(agg)
+            g_act = F.gelu(agg) if gelu_before_a else agg
         wa_cat = torch.empty((T * d, d), **f32)
         ba_cat = torch.empty(T * d, **f32)
         wa = self._ptrs("wa", [l.weight for l in self.a_linears], dev)
@@ -264,31 +287,77 @@ class HGTConv(nn.Module):
         _lib.call("hgt_concat_linears", wa.data_ptr(), ba.data_ptr(), T, d, d, wa_cat.data_ptr(), ba_cat.data_ptr(), st)
         o = torch.empty((N, d), **f32)
         with self._stage("upd_linear"):
-            self._typed_linear(g_act, d, wa_cat, ba_cat, d, d, lt.upd_groups, o, self.linear_impl, st)
+            if fuse_split:
+                g_dev, g_host, n_g, c_dev = lt.upd_groups
+                wsb = ctypes.c_size_t()
+                _lib.call("hgt_typed_linear_presplit_workspace_bytes", g_host.ctypes.data, n_g, d, d, ctypes.byref(wsb))
+                ws2 = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+                _lib.call("hgt_typed_linear_presplit", g_hi.data_ptr(), g_lo.data_ptr(), wa_cat.data_ptr(),
+                          ba_cat.data_ptr(), d, d, g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(),
+                          o.data_ptr(), ws2.data_ptr(), ws2.numel(), st)
+            else:
+                self._typed_linear(g_act, d, wa_cat, ba_cat, d, d, lt.upd_groups, o, self.linear_impl, st)
         if self.training and self.drop.p > 0:
             o = self.drop(o)                                       # conv.py:125 (train mode only)
-        norm_w = norm_b = None
+        return dict(plan=plan, lt=lt, x_sorted=x_sorted, w_cat=w_cat, proj=proj, kvr=kvr, agg=agg, o=o, stats=stats,
+                    att=att, N=N, d=d, T=T, st=st)
+
+
+class DenseHGTConv(HGTConv):
+    """Reference conv.py:143-280: the same message() as HGTConv (same typed projections, relation transforms,
+    softmax by destination, aggregation => the same CUDA kernels), but update() is
+        y = LayerNorm_t(a_linear_t(agg) + x)                         (no gelu, no skip gate; conv.py:261-266)
+        out = out_norm(out_linear(gelu(mid_linear(y))) + y)          (shared 2-layer FFN; conv.py:273-274)
+    The message/aggregate part and the three linears run through the C ABI (edge kernel, tcgen05 typed GEMM);
+    the residual / LayerNorm / gelu glue of this variant is torch elementwise code.
+    Parameter names match the reference (mid_linear, out_linear, out_norm; no `skip`).  Inference path only."""
+    _has_skip = False
+
+    def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
+                 use_RTE=True, **kwargs):
+        super().__init__(in_dim, out_dim, num_types, num_relations, n_heads, dropout, use_norm, use_RTE, **kwargs)
+        self.mid_linear = nn.Linear(out_dim, out_dim * 2)
+        self.out_linear = nn.Linear(out_dim * 2, out_dim)
+        self.out_norm = nn.LayerNorm(out_dim)
+
+    def forward(self, node_inp, node_type, edge_index, edge_type, edge_time=None):
+        self._check_inputs(node_inp, edge_time)
+        if torch.is_grad_enabled() and (node_inp.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("pyhgt_b200.DenseHGTConv: inference only (call under torch.no_grad())")
+        c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att=self.keep_att, save=False,
+                       active_per_type=None, gelu_before_a=False)
+        self.att = c["att"]
+        plan, o, x, N, d, T, st = c["plan"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
+        y = o + x                                                         # conv.py:261
         if self.use_norm:
-            norm_w = torch.stack([n.weight for n in self.norms]).contiguous()
-            norm_b = torch.stack([n.bias for n in self.norms]).contiguous()
-        out = torch.empty((N, d), **f32)
-        ev_e = self._stage("update_epilogue")
-        ev_e.__enter__()
-        _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
-                  self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
-                  None if plan.sorted_types else plan.perm.data_ptr(), _lib.ptr(lt.type_active_dev), N, d,
-                  out.data_ptr(), st)
-        ev_e.__exit__()
-        saved = None
-        if save:
-            saved = dict(plan=plan, lt=lt, x_sorted=x_sorted, w_cat=w_cat, proj=proj, kvr=kvr, agg=agg, o=o,
-                         stats=stats)
-        return out, att, saved
+            for t in range(T):
+                r = slice(plan.type_row0[t], plan.type_row0[t + 1])
+                if r.stop > r.start:
+                    y[r] = F.layer_norm(y[r], (d,), self.norms[t].weight, self.norms[t].bias, 1e-5)
+        n_known = plan.type_row0[T]
+        one = lambda m_, k_, w_: _plan._pack_groups([(0, m_, 0, 1, 0, 1)], [(0, w_)], y.device)
+        key = ("dense_ffn", d, n_known)
+        tabs = plan._layer_tables.get(key)
+        if tabs is None:
+            tabs = plan._layer_tables[key] = (one(n_known, d, 2 * d), one(n_known, 2 * d, d))
+        hmid = torch.empty((N, 2 * d), dtype=torch.float32, device=y.device)
+        self._typed_linear(y, d, self.mid_linear.weight, self.mid_linear.bias, d, 2 * d, tabs[0], hmid,
+                           self.linear_impl, st)
+        hmid = F.gelu(hmid)
+        z = torch.empty((N, d), dtype=torch.float32, device=y.device)
+        self._typed_linear(hmid, 2 * d, self.out_linear.weight, self.out_linear.bias, 2 * d, d, tabs[1], z,
+                           self.linear_impl, st)
+        res = F.layer_norm(z + y, (d,), self.out_norm.weight, self.out_norm.bias, 1e-5)   # conv.py:273-274
+        if n_known < N:
+            res[n_known:] = 0                                             # unknown-type rows stay zero (conv.py:256)
+        if not plan.sorted_types:
+            res = res.index_select(0, plan.rank.long())
+        return res
 
 
 class GeneralConv(nn.Module):
-    """String-keyed dispatch, reference conv.py:303-323.  'hgt' resolves to the CUDA HGTConv above;
-    the other convolution kinds are not on the hot path and raise."""
+    """String-keyed dispatch, reference conv.py:303-323.  'hgt' and 'dense_hgt' resolve to the CUDA layers above;
+    'gcn' / 'gat' are PyG library layers, not this path, and raise."""
 
     def __init__(self, conv_name, in_hid, out_hid, num_types, num_relations, n_heads, dropout, use_norm=True,
                  use_RTE=True):
@@ -296,8 +365,11 @@ class GeneralConv(nn.Module):
         self.conv_name = conv_name
         if self.conv_name == 'hgt':
             self.base_conv = HGTConv(in_hid, out_hid, num_types, num_relations, n_heads, dropout, use_norm, use_RTE)
+        elif self.conv_name == 'dense_hgt':
+            self.base_conv = DenseHGTConv(in_hid, out_hid, num_types, num_relations, n_heads, dropout, use_norm,
+                                          use_RTE)
         else:
-            raise NotImplementedError("pyhgt_b200 implements conv_name='hgt' only (got %r)" % conv_name)
+            raise NotImplementedError("pyhgt_b200 implements conv_name 'hgt' and 'dense_hgt' only (got %r)" % conv_name)
 
     def forward(self, meta_xs, node_type, edge_index, edge_type, edge_time):
         return self.base_conv(meta_xs, node_type, edge_index, edge_type, edge_time)

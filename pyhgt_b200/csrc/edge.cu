@@ -16,6 +16,8 @@
 //                      ring with mbarrier transaction counting; the warp issues STAGES rows ahead.
 // Roofline: HBM-bound; algorithmic bytes per edge = 2*d*4 (row) + 4 (kv_row) [+4 rte_row, +2*d*4 from L2]
 // and per destination d*4 (Q) + d*4 (agg) + 4 (row_ptr).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -35,7 +37,9 @@ struct EdgeParams {
   int32_t n_tiles;
   int32_t d, H, DK, LPH, lph_shift;
   int32_t apply_gelu;
-  float* agg_out;
+  float* agg_out;            // nullptr when only the split bf16 copy is wanted
+  __nv_bfloat16* g_hi;       // optional: result as bf16 hi/lo split (operand of the tcgen05 a_linear GEMM)
+  __nv_bfloat16* g_lo;
   float* att_out;            // nullptr unless requested
   float* stats_out;          // nullptr unless requested
   float* partial;            // [n_split][2*H + d]
@@ -76,6 +80,26 @@ __device__ __forceinline__ void store_vec(float* p, const float (&src)[VEC]) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) f[i] = src[i];
   *reinterpret_cast<V*>(p) = v;
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&src)[VEC]) {
+  __nv_bfloat16 h[VEC], l[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    h[i] = __float2bfloat16_rn(src[i]);
+    l[i] = __float2bfloat16_rn(src[i] - __bfloat162float(h[i]));
+  }
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<uint2*>(l);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(hi) = *reinterpret_cast<uint32_t*>(h);
+    *reinterpret_cast<uint32_t*>(lo) = *reinterpret_cast<uint32_t*>(l);
+  } else {
+    hi[0] = h[0];
+    lo[0] = l[0];
+  }
 }
 
 __device__ __forceinline__ float head_reduce(float v, int lph) {
@@ -145,7 +169,8 @@ __device__ __forceinline__ void finalize_destination(const EdgeParams& p, const 
         float x = st.acc[t][v] * inv;
         r[v] = p.apply_gelu ? hgt_gelu_erf(x) : x;
       }
-      store_vec<VEC>(orow + o, r);
+      if (p.agg_out) store_vec<VEC>(orow + o, r);
+      if (p.g_hi) store_split_bf16<VEC>(p.g_hi + (int64_t)dst * p.d + o, p.g_lo + (int64_t)dst * p.d + o, r);
     }
   }
   if (p.stats_out && lm.head_ok && lm.sub == 0) {
@@ -502,7 +527,13 @@ k_merge_partials(EdgeParams p, const int32_t* __restrict__ hubs, int n_hubs) {
 #pragma unroll
         for (int w = 0; w < 32; ++w) t += s_red[w][lane];
         t *= s_inv[c / p.DK];
-        p.agg_out[(int64_t)dst * p.d + c] = p.apply_gelu ? hgt_gelu_erf(t) : t;
+        t = p.apply_gelu ? hgt_gelu_erf(t) : t;
+        if (p.agg_out) p.agg_out[(int64_t)dst * p.d + c] = t;
+        if (p.g_hi) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(t);
+          p.g_hi[(int64_t)dst * p.d + c] = h;
+          p.g_lo[(int64_t)dst * p.d + c] = __float2bfloat16_rn(t - __bfloat162float(h));
+        }
       }
       __syncthreads();
     }
@@ -561,13 +592,16 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
                                 const int32_t* tiles, int32_t n_tiles, int32_t n_split_tiles, const int32_t* hubs,
                                 int32_t n_hubs, int64_t n_nodes,
                                 int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu, float* agg_out,
-                                float* att_out, float* stats_out, void* workspace, size_t workspace_bytes,
-                                int32_t variant, void* stream_) {
+                                float* att_out, float* stats_out, void* g_hi, void* g_lo, void* workspace,
+                                size_t workspace_bytes, int32_t variant, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   (void)n_edges;
   HGT_REQUIRE(n_heads >= 1 && n_heads <= 32, "hgt_edge_forward: n_heads=%d unsupported (1..32)", n_heads);
   HGT_REQUIRE(d % n_heads == 0, "hgt_edge_forward: d=%d not divisible by n_heads=%d", d, n_heads);
   HGT_REQUIRE((kvr != nullptr) == (rte_row != nullptr), "hgt_edge_forward: kvr and rte_row must go together");
+  HGT_REQUIRE((g_hi != nullptr) == (g_lo != nullptr) && (agg_out != nullptr || g_hi != nullptr),
+              "hgt_edge_forward: need agg_out and/or the (g_hi, g_lo) pair");
+  HGT_REQUIRE(g_hi == nullptr || d % 8 == 0, "hgt_edge_forward: split output needs d %% 8 == 0 (d=%d)", d);
   size_t need = 0;
   hgt_edge_workspace_bytes(n_split_tiles, d, n_heads, &need);
   HGT_REQUIRE(workspace_bytes >= need, "hgt_edge_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -583,6 +617,7 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
   p.lph_shift = shift;
   p.apply_gelu = apply_gelu;
   p.agg_out = agg_out; p.att_out = att_out; p.stats_out = stats_out;
+  p.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); p.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo);
   p.tile_counter = reinterpret_cast<int32_t*>(workspace);
   p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
 

@@ -845,10 +845,44 @@ size_t hgt_typed_linear_tc_workspace(const hgt_lin_group* h_groups, int32_t n_gr
   return 4 * 256 + 2 * hgt_align_up((size_t)a_rows * Kp * 2, 256) + 2 * hgt_align_up((size_t)w_rows * Kp * 2, 256);
 }
 
+static int tc_run(const float* A, int64_t lda, const __nv_bfloat16* a_hi_in, const __nv_bfloat16* a_lo_in,
+                  const float* W, const float* bias, int32_t K, int32_t cb_width, const hgt_lin_group* groups,
+                  const hgt_lin_group* h_groups, int32_t n_groups, const hgt_lin_cblock* cblocks, float* out,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float* bias, int32_t K, int32_t cb_width,
                         const hgt_lin_group* groups, const hgt_lin_group* h_groups, int32_t n_groups,
                         const hgt_lin_cblock* cblocks, float* out, void* workspace, size_t workspace_bytes,
                         cudaStream_t st) {
+  return tc_run(A, lda, nullptr, nullptr, W, bias, K, cb_width, groups, h_groups, n_groups, cblocks, out, workspace,
+                workspace_bytes, st);
+}
+
+extern "C" int hgt_typed_linear_presplit_workspace_bytes(const hgt_lin_group* h_groups, int32_t n_groups, int32_t K,
+                                                         int32_t cb_width, size_t* out_bytes) {
+  HGT_REQUIRE(out_bytes && (h_groups || n_groups == 0), "hgt_typed_linear_presplit_workspace_bytes: NULL argument");
+  *out_bytes = n_groups > 0 ? hgt_typed_linear_tc_workspace(h_groups, n_groups, K, cb_width) : 0;
+  return 0;
+}
+
+extern "C" int hgt_typed_linear_presplit(const void* a_hi, const void* a_lo, const float* W, const float* bias,
+                                         int32_t K, int32_t cb_width, const hgt_lin_group* groups,
+                                         const hgt_lin_group* h_groups, int32_t n_groups,
+                                         const hgt_lin_cblock* cblocks, float* out, void* workspace,
+                                         size_t workspace_bytes, void* stream_) {
+  HGT_REQUIRE(a_hi && a_lo, "hgt_typed_linear_presplit: NULL operand");
+  HGT_REQUIRE(K % 8 == 0 && hgt_typed_linear_tc_supported(K, K, cb_width),
+              "hgt_typed_linear_presplit: unsupported shape K=%d cb_width=%d", K, cb_width);
+  if (n_groups == 0) return 0;
+  return tc_run(nullptr, 0, reinterpret_cast<const __nv_bfloat16*>(a_hi), reinterpret_cast<const __nv_bfloat16*>(a_lo),
+                W, bias, K, cb_width, groups, h_groups, n_groups, cblocks, out, workspace, workspace_bytes,
+                (cudaStream_t)stream_);
+}
+
+static int tc_run(const float* A, int64_t lda, const __nv_bfloat16* a_hi_in, const __nv_bfloat16* a_lo_in,
+                  const float* W, const float* bias, int32_t K, int32_t cb_width, const hgt_lin_group* groups,
+                  const hgt_lin_group* h_groups, int32_t n_groups, const hgt_lin_cblock* cblocks, float* out,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const int BN = pick_bn(cb_width);
   HGT_REQUIRE(BN > 0, "hgt_typed_linear(tc): cb_width=%d has no multiple-of-16 tile", cb_width);
   const int Kp = (K + 7) / 8 * 8;
@@ -864,8 +898,13 @@ int hgt_typed_linear_tc(const float* A, int64_t lda, const float* W, const float
   __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(p);
   {
     int64_t n = a_rows * (Kp / 4);
-    if (n > 0) k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, lda, a_rows, K, Kp, a_hi, a_lo);
-    HGT_LAUNCH_CHECK();
+    if (a_hi_in) {
+      a_hi = const_cast<__nv_bfloat16*>(a_hi_in);            // split by the producer (e.g. the edge kernel)
+      a_lo = const_cast<__nv_bfloat16*>(a_lo_in);
+    } else if (n > 0) {
+      k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, lda, a_rows, K, Kp, a_hi, a_lo);
+      HGT_LAUNCH_CHECK();
+    }
     n = w_rows * (Kp / 4);
     if (n > 0) k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, K, w_rows, K, Kp, w_hi, w_lo);
     HGT_LAUNCH_CHECK();

@@ -385,3 +385,21 @@ def test_gnn_stack_matches_reference_model_golden():
         out = m(fx["node_feature"].to(dev), fx["node_type"].to(dev), fx["edge_time"].to(dev),
                 fx["edge_index"].to(dev), fx["edge_type"].to(dev))
     _close(out, fx["out"], "GNN 2-layer out")
+
+
+def test_dense_hgt_conv_matches_reference_golden():
+    """DenseHGTConv (conv.py:143-280) — same message kernels, residual/LayerNorm/FFN update."""
+    import pyhgt_b200
+    dev = _dev()
+    fx = load_golden("dense_hgt")
+    c = fx["cfg"]
+    g = pyhgt_b200.GeneralConv('dense_hgt', c["in_dim"], c["out_dim"], c["num_types"], c["num_relations"], c["n_heads"],
+                               0.2, c["use_norm"], c["use_RTE"])
+    m = g.base_conv
+    m.load_state_dict(fx["state_dict"], strict=True)
+    g = g.to(dev).eval()
+    with torch.no_grad():
+        out = g(fx["node_inp"].to(dev), fx["node_type"].to(dev), fx["edge_index"].to(dev), fx["edge_type"].to(dev),
+                fx["edge_time"].to(dev))
+    _close(out, fx["out"], "dense_hgt out")
+    _close(m.att, fx["att"], "dense_hgt att", atol=1e-4)

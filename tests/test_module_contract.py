@@ -58,8 +58,19 @@ def test_parameter_names_equal_reference_module():
 def test_general_conv_dispatch():
     g = pyhgt_b200.GeneralConv('hgt', 32, 32, 2, 3, 4, 0.2, True, False)
     assert isinstance(g.base_conv, pyhgt_b200.HGTConv) and g.base_conv.use_RTE is False
+    d = pyhgt_b200.GeneralConv('dense_hgt', 32, 32, 2, 3, 4, 0.2, True, True)
+    assert isinstance(d.base_conv, pyhgt_b200.DenseHGTConv) and not hasattr(d.base_conv, "skip")
     with pytest.raises(NotImplementedError):
         pyhgt_b200.GeneralConv('gcn', 32, 32, 2, 3, 4, 0.2)
+
+
+def test_dense_hgt_state_dict_matches_reference_fixture():
+    fx = load_golden("dense_hgt")
+    c = fx["cfg"]
+    m = pyhgt_b200.DenseHGTConv(c["in_dim"], c["out_dim"], c["num_types"], c["num_relations"], c["n_heads"], 0.2,
+                                c["use_norm"], c["use_RTE"])
+    assert list(m.state_dict().keys()) == list(fx["state_dict"].keys())
+    m.load_state_dict(fx["state_dict"], strict=True)
 
 
 def test_gnn_wrapper_state_dict_matches_reference_fixture():
