@@ -209,6 +209,16 @@ def main_ours(args, rank, local_rank, world):
         def step():
             return shard.forward(conv, x_own)
         n_dst_local, e_local = shard.n_owned, shard.n_local_edges
+        halo_diff = None
+        if args.verify_halo:
+            keep = shard.halo_mode
+            with torch.no_grad():
+                shard.halo_mode = "nccl"; o1 = shard.forward(conv, x_own).clone()
+                shard.halo_mode = "p2p"; o2 = shard.forward(conv, x_own).clone()
+            shard.halo_mode = keep
+            dmax = (o1 - o2).abs().max().reshape(1)
+            dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+            halo_diff = dmax.item()
 
     with torch.no_grad():
         sampler = ClockSampler(local_rank)
@@ -359,11 +369,12 @@ def main_ours(args, rank, local_rank, world):
                                    "step in e2e",
                            "parallelism": "single GPU" if world == 1 else
                                           "dst-node sharding x%d, halo source rows per step via %s" % (
-                                              world, "one NCCL all_to_all_single" if (args.halo or os.environ.get("HGT_HALO", "nccl")) == "nccl"
-                                              else "fused NVLink peer-memory pull kernel (symmetric memory)"),
+                                              world, "one NCCL all_to_all_single" if shard.halo_mode == "nccl"
+                                              else "fused NVLink peer-memory pull kernel (torch symmetric memory)"),
                            "linear": "tcgen05 split-bf16 (3 products, fp32 accumulate)", "edge": "TMA bulk-copy ring"},
                 "roofline": roofline, "roofline_linear": roofline_linear,
-                "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()}, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
+                "halo_modes_max_abs_diff": halo_diff if world > 1 else None, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,6 +388,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="graph scale (1.0 = BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-halo", action="store_true",
+                    help="multi-GPU only: run one step with both halo exchanges and report the max abs difference")
     ap.add_argument("--halo", default=None, choices=["nccl", "p2p"],
                     help="multi-GPU halo exchange: one NCCL all_to_all (default) or the fused peer-memory pull kernel")
     args = ap.parse_args()

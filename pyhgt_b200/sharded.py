@@ -65,7 +65,8 @@ class ShardedGraph:
     num_types: int
     num_relations: int
     group: object = None
-    halo_mode: str = "nccl"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer memory
+    halo_mode: str = "auto"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer
+                                      # memory; "auto": p2p on CUDA when symmetric memory works, else nccl
     _symm: object = None
 
     @staticmethod
@@ -116,7 +117,8 @@ class ShardedGraph:
         send_splits = [int(x.numel()) for x in send_lists]
         send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, dtype=torch.int64)
         active = torch.bincount(tkey[owned], minlength=num_types + 1).tolist()
-        mode = halo_mode or os.environ.get("HGT_HALO", "nccl")
+        # "auto" (default): fused peer-memory pull on CUDA, NCCL all_to_all if symmetric memory is unavailable
+        mode = halo_mode or os.environ.get("HGT_HALO", "auto")
         return ShardedGraph(rank=rank, world=world, device=device, n_owned=n_owned, n_halo=n_halo,
                             n_local_edges=int(e_sel.numel()), owned_global=owned, halo_global=halo,
                             local_global=local_global, node_type=node_type[local_global].to(device),
@@ -143,8 +145,19 @@ class ShardedGraph:
 
     def exchange(self, x_own):
         """[n_owned, d] owned rows -> [n_local, d] local rows in local (type-sorted) order."""
-        if self.halo_mode == "p2p" and x_own.is_cuda and self.world > 1:
-            return self._exchange_p2p(x_own)
+        if self.halo_mode in ("p2p", "auto") and x_own.is_cuda and self.world > 1:
+            if self.halo_mode == "p2p":
+                return self._exchange_p2p(x_own)
+            try:
+                out = self._exchange_p2p(x_own)
+                self.halo_mode = "p2p"
+                return out
+            except Exception as exc:                                   # noqa: BLE001 — both paths are GPU paths
+                import warnings
+                warnings.warn("pyhgt_b200: symmetric-memory halo exchange unavailable (%s); using NCCL all_to_all" % exc)
+                self.halo_mode = "nccl"
+        elif self.halo_mode == "auto":
+            self.halo_mode = "nccl"
         d = x_own.shape[1]
         if getattr(self, "_send_idx32", None) is None:
             self._send_idx32 = self.send_idx.to(torch.int32)
