@@ -1,0 +1,30 @@
+"""Latency of one HGTConv forward on a sampled-subgraph-sized input (BASELINE config 1: 1k nodes / 5k edges),
+with and without the per-graph plan build — the regime of pyHGT's own training loop (new graph every batch)."""
+import os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyhgt_b200 import HGTConv, synth, clear_plan_cache
+
+dev = torch.device("cuda:0")
+for name, g, d, H in (("c1", synth.make_c1(), 64, 4), ("oag-batch", synth.make_oag_shaped(0.05), 400, 8)):
+    torch.manual_seed(0)
+    m = HGTConv(d, d, g.num_types, g.num_relations, H, 0.2, True, True).to(dev).eval()
+    x = torch.randn(g.num_nodes, d, device=dev)
+    nt, ei, et, tm = (t.to(dev) for t in (g.node_type, g.edge_index, g.edge_type, g.edge_time))
+    with torch.no_grad():
+        for _ in range(5):
+            m(x, nt, ei, et, tm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            m(x, nt, ei, et, tm)
+        torch.cuda.synchronize()
+        warm = (time.perf_counter() - t0) / 50 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(20):
+            clear_plan_cache()
+            m(x, nt, ei, et, tm)
+        torch.cuda.synchronize()
+        cold = (time.perf_counter() - t0) / 20 * 1e3
+    print("%s: N=%d E=%d d=%d  forward %.3f ms (plan cached)  %.3f ms (plan rebuilt)  -> %.1f / %.1f M edges/s"
+          % (name, g.num_nodes, g.num_edges, d, warm, cold, g.num_edges / warm / 1e3, g.num_edges / cold / 1e3))
