@@ -403,3 +403,54 @@ def test_dense_hgt_conv_matches_reference_golden():
                 fx["edge_time"].to(dev))
     _close(out, fx["out"], "dense_hgt out")
     _close(m.att, fx["att"], "dense_hgt att", atol=1e-4)
+
+
+def test_full_size_c2_properties_and_sampled_rows():
+    """BASELINE config 2 at FULL size (1.94 M nodes, 21.1 M edges, d=256): (a) the output rows of 3000 sampled
+    destinations equal the CPU oracle run on their 1-hop induced subgraph (a destination's row depends only on its
+    in-edges and their sources), (b) per-destination attention sums to 1, (c) isolated destinations take the
+    bias path, (d) both edge-kernel variants agree."""
+    import pyhgt_b200
+    dev = _dev()
+    g = synth.make_mag_shaped(1.0, seed=2)
+    N, E, d, H = g.num_nodes, g.num_edges, 256, 8
+    torch.manual_seed(0)
+    m = pyhgt_b200.HGTConv(d, d, 4, 4, H, 0.2, True, False).eval()
+    x = torch.randn(N, d, generator=torch.Generator().manual_seed(1))
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(dev)
+    nt, ei, et = g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev)
+    xd = x.to(dev)
+    old_keep = pyhgt_b200.HGTConv.keep_att
+    try:
+        pyhgt_b200.HGTConv.keep_att = True
+        with torch.no_grad():
+            m.edge_variant = 2
+            out = m(xd, nt, ei, et)
+            att = m.att
+            sums = torch.zeros(N, H, device=dev).index_add_(0, ei[1], att)
+            deg = torch.bincount(ei[1], minlength=N)
+            assert torch.allclose(sums[deg > 0], torch.ones_like(sums[deg > 0]), atol=1e-4)
+            assert torch.all(sums[deg == 0] == 0)
+            del att, sums
+            pyhgt_b200.HGTConv.keep_att = False
+            m.edge_variant = 1
+            out1 = m(xd, nt, ei, et)
+        assert torch.isfinite(out).all()
+        _close(out1, out, "variant 1 vs 2 at full size", atol=1e-5)
+        del out1
+    finally:
+        pyhgt_b200.HGTConv.keep_att = old_keep
+    # (a) sampled destinations vs the oracle on the induced 1-hop subgraph
+    gen = torch.Generator().manual_seed(5)
+    has_in = (deg > 0).cpu().nonzero(as_tuple=True)[0]
+    sample = torch.cat([has_in[torch.randperm(has_in.numel(), generator=gen)[:2500]],
+                        (deg == 0).cpu().nonzero(as_tuple=True)[0][:500]])
+    sel = torch.zeros(N, dtype=torch.bool); sel[sample] = True
+    e_sel = sel[g.edge_index[1]].nonzero(as_tuple=True)[0]
+    nodes = torch.unique(torch.cat([sample, g.edge_index[0, e_sel]]))
+    local = torch.full((N,), -1, dtype=torch.int64); local[nodes] = torch.arange(nodes.numel())
+    sub_ei = torch.stack([local[g.edge_index[0, e_sel]], local[g.edge_index[1, e_sel]]])
+    ref, _ = hgt_oracle.hgt_forward_ref_port(params, x[nodes], g.node_type[nodes], sub_ei, g.edge_type[e_sel], None,
+                                             num_types=4, num_relations=4, n_heads=H, use_norm=True, use_RTE=False)
+    _close(out[sample.to(dev)], ref[local[sample]], "full-size C2: sampled destination rows vs oracle")
