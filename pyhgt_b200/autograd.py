@@ -4,14 +4,16 @@ OAG/train_paper_field.py:249 ``loss.backward()``).
 The graph-dependent, memory-bound part — score / softmax-by-destination / weighted aggregation — is ONE custom
 autograd.Function whose forward and backward are the hand-written kernels ``hgt_edge_forward`` /
 ``hgt_edge_backward`` on the cached CSR plan (no per-edge intermediates are kept: backward recomputes the
-softmax weights from the saved per-destination (max, sum)).  The dense typed linears, the relation-matrix fold
-and the gated-skip/LayerNorm around it run as ordinary differentiable torch ops in this round (cuBLAS GEMMs),
-so gradients reach ``node_inp`` and every parameter of conv.py:28-54 including ``emb.*``.  The inference path
+softmax weights from the saved per-destination (max, sum)).  The typed linears (Q / K' / V' projection, a_linears)
+run FORWARD through the same tcgen05 grouped GEMM as inference (``_TypedLinear``); their backward (dX, dW, db) uses
+cuBLAS fp32 GEMMs on strided views this round.  The relation-matrix fold and the gated-skip / LayerNorm are small
+differentiable torch ops, so gradients reach ``node_inp`` and every parameter of conv.py:28-54 including ``emb.*``.  The inference path
 (``torch.no_grad``) does not come through here: it uses the fused tcgen05 / epilogue kernels in conv.py.
 """
 import ctypes
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -66,6 +68,57 @@ class _EdgeAttention(torch.autograd.Function):
         return dq, dkv, dkvr, None, None, None, None
 
 
+_CBLOCKS_HOST = {}
+
+
+class _TypedLinear(torch.autograd.Function):
+    """Grouped typed linear through the C ABI (``hgt_typed_linear``: tcgen05 split-bf16 when the shape allows).
+    forward : out_flat[cblock c of group g][m, :] = A[rows_g] @ W_cat[rows of (g, c)]^T + b_cat
+    backward: dA / dW_cat / db_cat with cuBLAS fp32 GEMMs on strided views of the flat gradient buffer (the
+              native split-bf16 dX / dW kernels are future work)."""
+
+    @staticmethod
+    def forward(ctx, a, w_cat, b_cat, module, table, width, out_elems, impl):
+        g_dev, g_host, n_g, c_dev = table
+        a = a.contiguous()
+        w_cat = w_cat.contiguous()
+        out = torch.zeros(out_elems, dtype=torch.float32, device=a.device)
+        module._typed_linear(a, a.shape[1], w_cat, b_cat, a.shape[1], width, table, out, impl, _stream())
+        ctx.table, ctx.width, ctx.has_bias = table, width, b_cat is not None
+        key = (c_dev.data_ptr(), c_dev.numel())
+        if key not in _CBLOCKS_HOST:                                  # column-block table on the host (once per table)
+            _CBLOCKS_HOST[key] = np.frombuffer(c_dev.cpu().numpy().tobytes(), dtype=_lib.LIN_CBLOCK_DTYPE)
+        ctx.cblocks_host = _CBLOCKS_HOST[key]
+        ctx.save_for_backward(a, w_cat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, w_cat = ctx.saved_tensors
+        _, g_host, n_g, _ = ctx.table
+        width, K = ctx.width, a.shape[1]
+        da = torch.zeros_like(a)
+        dw = torch.zeros_like(w_cat)
+        db = torch.zeros(w_cat.shape[0], dtype=torch.float32, device=a.device) if ctx.has_bias else None
+        dout = dout.contiguous()
+        for gi in range(n_g):
+            g = g_host[gi]
+            r0, m = int(g["a_row0"]), int(g["m"])
+            if m == 0:
+                continue
+            a_g = a[r0:r0 + m]
+            for c in range(int(g["n_cblocks"])):
+                cb = ctx.cblocks_host[int(g["cb_first"]) + c]
+                off, ld = int(cb["out_off"]), int(cb["ld"])
+                d_blk = torch.as_strided(dout, (m, width), (ld, 1), off)            # [m, width] view
+                w0 = int(g["w_row0"]) + c * width
+                da[r0:r0 + m].addmm_(d_blk, w_cat[w0:w0 + width])
+                dw[w0:w0 + width].addmm_(d_blk.t(), a_g)
+                if db is not None and int(g["has_bias"]):
+                    db[w0:w0 + width] += d_blk.sum(0)
+        return da, dw, db, None, None, None, None, None
+
+
 def _fold(w, b, rel, scale, H, dk):
     """W'[h*dk+c, :] = scale[h] * sum_a rel[h,a,c] * W[h*dk+a, :]  (and the same for the bias): the per-head
     right-multiplication of conv.py:98/104 moved into the weights."""
@@ -88,24 +141,29 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
     x = node_inp if plan.sorted_types else node_inp.index_select(0, plan.perm.long())
     rows = [slice(plan.type_row0[t], plan.type_row0[t + 1]) for t in range(T)]
 
-    # typed projections with the relation matrices folded in (pairs are enumerated type-major: plan.pairs)
+    # typed projections with the relation matrices folded in.  W_cat / b_cat are assembled with differentiable torch
+    # ops (tiny: the fold is O(P * d * d_in * d_k)); the big grouped GEMM runs through the C ABI (_TypedLinear).
+    lt = _plan.layer_tables(plan, d_in, d)
+    pairs_of_type = [[] for _ in range(T)]
+    for p, (s_, _) in enumerate(plan.pairs):
+        pairs_of_type[s_].append(p)
     folded = {}
-    for p, (s, r) in enumerate(plan.pairs):
-        kw, kb = _fold(m.k_linears[s].weight, m.k_linears[s].bias, m.relation_att[r],
+    for p, (s_, r) in enumerate(plan.pairs):
+        kw, kb = _fold(m.k_linears[s_].weight, m.k_linears[s_].bias, m.relation_att[r],
                        m.relation_pri[r] / math.sqrt(dk), H, dk)
-        vw, vb = _fold(m.v_linears[s].weight, m.v_linears[s].bias, m.relation_msg[r], None, H, dk)
+        vw, vb = _fold(m.v_linears[s_].weight, m.v_linears[s_].bias, m.relation_msg[r], None, H, dk)
         folded[p] = (torch.cat([kw, vw], 0), torch.cat([kb, vb], 0))            # [2d, d_in]: K' rows then V' rows
-    q_parts, kv_parts = [], []
-    for t in range(T):
-        xt = x[rows[t]]
-        q_parts.append(F.linear(xt, m.q_linears[t].weight, m.q_linears[t].bias))
-    for p, (s, r) in enumerate(plan.pairs):
-        kv_parts.append(F.linear(x[rows[s]], folded[p][0], folded[p][1]))       # [N_s, 2d] = [K'|V']
-    tail = N - plan.type_row0[T]
-    if tail:
-        q_parts.append(x.new_zeros(tail, d))                                     # nodes of unknown type: never used
-    q = torch.cat(q_parts, 0)
-    kv = torch.cat(kv_parts + [x.new_zeros(1, 2 * d)], 0)
+    w_parts, b_parts = [], []
+    for t in range(T):                                                          # same row order as plan.layer_tables
+        w_parts.append(m.q_linears[t].weight)
+        b_parts.append(m.q_linears[t].bias)
+        for p in pairs_of_type[t]:
+            w_parts.append(folded[p][0])
+            b_parts.append(folded[p][1])
+    w_cat, b_cat = torch.cat(w_parts, 0), torch.cat(b_parts, 0)
+    proj = _TypedLinear.apply(x, w_cat, b_cat, m, lt.proj_groups, d, lt.proj_elems, m.linear_impl)
+    q = proj[lt.q_off:lt.q_off + N * d].view(N, d)
+    kv = proj[lt.kv_off:lt.kv_off + (plan.kv_rows + 1) * 2 * d].view(plan.kv_rows + 1, 2 * d)
     kvr = None
     if m.use_RTE:
         rt = F.linear(m.emb.emb.weight, m.emb.lin.weight, m.emb.lin.bias)        # [240, d_in], conv.py:299
@@ -115,9 +173,12 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
     m.att = att
 
     g = F.gelu(agg)                                                              # conv.py:119
+    wa_cat = torch.cat([l.weight for l in m.a_linears], 0)
+    ba_cat = torch.cat([l.bias for l in m.a_linears], 0)
+    o_all = _TypedLinear.apply(g, wa_cat, ba_cat, m, lt.upd_groups, d, N * d, m.linear_impl).view(N, d)
     outs = []
     for t in range(T):
-        o = m.drop(m.a_linears[t](g[rows[t]]))                                   # conv.py:125
+        o = m.drop(o_all[rows[t]])                                               # conv.py:125
         alpha = torch.sigmoid(m.skip[t])                                         # conv.py:129
         y = o * alpha + x[rows[t]] * (1 - alpha)
         if m.use_norm:

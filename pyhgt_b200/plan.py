@@ -22,8 +22,9 @@ import torch
 from . import _lib
 
 RTE_MAX_LEN = 240            # conv.py:287
-TILE_TARGET_EDGES = 64       # edges per work tile (cost units: see csrc/plan.cu)
-TILE_SPLIT_EDGES = 1024      # destinations with more in-edges than this are split across warps
+import os as _os
+TILE_TARGET_EDGES = int(_os.environ.get("HGT_TILE_EDGES", "64"))      # edges per work tile (cost units: csrc/plan.cu)
+TILE_SPLIT_EDGES = int(_os.environ.get("HGT_SPLIT_EDGES", "1024"))    # larger destinations are split across warps
 
 
 def _stream():
