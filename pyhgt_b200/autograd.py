@@ -169,6 +169,7 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
         rt = F.linear(m.emb.emb.weight, m.emb.lin.weight, m.emb.lin.bias)        # [240, d_in], conv.py:299
         kvr = torch.cat([F.linear(rt, folded[p][0]) for p in range(P)] + [x.new_zeros(1, 2 * d)], 0)
 
+    tail = N - plan.type_row0[T]                                                 # nodes of unknown type (conv.py:120)
     agg, att = _EdgeAttention.apply(q, kv, kvr, plan, H, bool(m.keep_att), m.edge_variant)
     m.att = att
 
