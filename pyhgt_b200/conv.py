@@ -183,7 +183,9 @@ class HGTConv(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
-                      active_per_type=None):
+                      active_per_type=None, out_map=None, out_rows=None):
+        """out_map / out_rows (sharded runs): int32 [N] map from rank-order row to output row and the number of output
+        rows; rows that are not active (halo sources) are never written, so the output holds exactly the owned rows."""
         c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
                        gelu_before_a=True)
         plan, lt, o, x_sorted, N, d, T, st = c["plan"], c["lt"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
@@ -192,12 +194,17 @@ class HGTConv(nn.Module):
         if self.use_norm:
             norm_w = torch.stack([n.weight for n in self.norms]).contiguous()
             norm_b = torch.stack([n.bias for n in self.norms]).contiguous()
-        out = torch.empty((N, d), **f32)
+        out = torch.empty((N if out_rows is None else out_rows, d), **f32)
+        if out_map is not None:
+            if not plan.sorted_types:
+                raise ValueError("out_map needs a type-sorted node order")
+            perm_ptr = out_map.data_ptr()
+        else:
+            perm_ptr = None if plan.sorted_types else plan.perm.data_ptr()
         with self._stage("update_epilogue"):
             _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
-                      self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b),
-                      None if plan.sorted_types else plan.perm.data_ptr(), _lib.ptr(lt.type_active_dev), N, d,
-                      out.data_ptr(), st)
+                      self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b), perm_ptr,
+                      _lib.ptr(lt.type_active_dev), N, d, out.data_ptr(), st)
         return out, c["att"], (c if save else None)
 
     def _core(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,

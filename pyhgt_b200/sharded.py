@@ -194,11 +194,18 @@ class ShardedGraph:
         from .conv import HGTConv
         with HGTConv._stage("halo_exchange"):
             x_local = self.exchange(x_own)
+        if x_local.is_cuda:
+            # the update epilogue writes each owned row straight to its position in owned_global order
+            if getattr(self, "_out_map", None) is None:
+                om = torch.full((self.n_owned + self.n_halo,), -1, dtype=torch.int32, device=x_local.device)
+                om[self.own_rows] = torch.arange(self.n_owned, dtype=torch.int32, device=x_local.device)
+                self._out_map = om
+            out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
+                                             self.edge_time if conv.use_RTE else None, want_att=False, save=False,
+                                             active_per_type=self.active_per_type, out_map=self._out_map,
+                                             out_rows=self.n_owned)
+            return out
         out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
                                          self.edge_time if conv.use_RTE else None, want_att=False, save=False,
                                          active_per_type=self.active_per_type)
-        with HGTConv._stage("collect_owned"):
-            if getattr(self, "_own_rows32", None) is None:
-                self._own_rows32 = self.own_rows.to(torch.int32)
-            res = self._gather(out, self._own_rows32, self.n_owned)
-        return res
+        return out.index_select(0, self.own_rows)

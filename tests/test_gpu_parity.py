@@ -300,6 +300,14 @@ def test_sharded_local_forward_matches_full_graph(world):
             out, _, _ = m._forward_impl(x_local, sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time,
                                         want_att=False, save=False, active_per_type=sh.active_per_type)
         _close(out[sh.own_rows], full[sh.owned_global], "rank %d/%d owned rows" % (rank, world), atol=1e-5)
+        # ShardedGraph.forward's direct-to-owned-order epilogue (world=1 exchange is the identity gather)
+        om = torch.full((sh.n_owned + sh.n_halo,), -1, dtype=torch.int32, device=dev)
+        om[sh.own_rows] = torch.arange(sh.n_owned, dtype=torch.int32, device=dev)
+        with torch.no_grad():
+            out2, _, _ = m._forward_impl(x_local, sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time,
+                                         want_att=False, save=False, active_per_type=sh.active_per_type,
+                                         out_map=om, out_rows=sh.n_owned)
+        _close(out2, full[sh.owned_global], "rank %d/%d direct owned-order output" % (rank, world), atol=1e-5)
 
 
 @pytest.mark.parametrize("name", ["c1_rte", "rand_t3r4_dk4"])
