@@ -183,11 +183,11 @@ class HGTConv(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
-                      active_per_type=None, out_map=None, out_rows=None):
+                      active_per_type=None, out_map=None, out_rows=None, x_split=None):
         """out_map / out_rows (sharded runs): int32 [N] map from rank-order row to output row and the number of output
         rows; rows that are not active (halo sources) are never written, so the output holds exactly the owned rows."""
         c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
-                       gelu_before_a=True)
+                       gelu_before_a=True, x_split=x_split)
         plan, lt, o, x_sorted, N, d, T, st = c["plan"], c["lt"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
         f32 = dict(dtype=torch.float32, device=o.device)
         norm_w = norm_b = None
@@ -208,7 +208,7 @@ class HGTConv(nn.Module):
         return out, c["att"], (c if save else None)
 
     def _core(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
-              gelu_before_a):
+              gelu_before_a, x_split=None):
         """Everything up to and including the typed a_linear: plan, weight fold, typed projections, fused edge kernel
         (gelu fused iff gelu_before_a and not save), a_linears.  Returns a dict of the intermediates."""
         dev = node_inp.device
@@ -250,7 +250,17 @@ class HGTConv(nn.Module):
         kv_tab = proj[lt.kv_off:]
         kv_tab[plan.kv_rows * 2 * d:].zero_()
         with self._stage("proj_linear"):
-            self._typed_linear(x_sorted, d_in, w_cat, b_cat, d_in, d, lt.proj_groups, proj, self.linear_impl, st)
+            if x_split is not None and plan.sorted_types:
+                # A operand already split by its producer (the fused halo pull): tensor-core GEMM without the split pass
+                g_dev, g_host, n_g, c_dev = lt.proj_groups
+                wsb = ctypes.c_size_t()
+                _lib.call("hgt_typed_linear_presplit_workspace_bytes", g_host.ctypes.data, n_g, d_in, d, ctypes.byref(wsb))
+                ws1 = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+                _lib.call("hgt_typed_linear_presplit", x_split[0].data_ptr(), x_split[1].data_ptr(), w_cat.data_ptr(),
+                          b_cat.data_ptr(), d_in, d, g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(),
+                          proj.data_ptr(), ws1.data_ptr(), ws1.numel(), st)
+            else:
+                self._typed_linear(x_sorted, d_in, w_cat, b_cat, d_in, d, lt.proj_groups, proj, self.linear_impl, st)
         kvr = None
         if self.use_RTE:
             # RT = lin(emb.weight) [240,d] (conv.py:299), then projected with every pair's K'/V' weights (no bias)

@@ -3,6 +3,7 @@
 // and scans use CUB device primitives (CUDA toolkit), everything else is hand-written.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -252,6 +253,35 @@ __global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_
   }
 }
 
+// Pull + convert: the halo rows are only ever consumed as the bf16 hi/lo operand split of the projection GEMM, so the
+// conversion is done while the row crosses NVLink; fp32 is kept only for the rows this rank owns (skip connection).
+__global__ void k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
+                                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank,
+                                  float4* __restrict__ out_f32, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const int owner = src_rank[r];
+    const float4* src = reinterpret_cast<const float4*>(peers[owner]) + (int64_t)src_row[r] * vec_per_row;
+    for (int c = lane; c < vec_per_row; c += 32) {
+      float4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + c));
+      if (owner == self_rank) out_f32[r * vec_per_row + c] = v;
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(f[j]);
+        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+      }
+      hi[r * vec_per_row + c] = *reinterpret_cast<uint2*>(h);
+      lo[r * vec_per_row + c] = *reinterpret_cast<uint2*>(l);
+    }
+  }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -400,6 +430,24 @@ extern "C" int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, co
   k_halo_pull<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(reinterpret_cast<const float* const*>(peer_ptrs_dev),
                                                                  src_rank, src_row, n_rows, width / 4,
                                                                  reinterpret_cast<float4*>(out));
+  HGT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row,
+                                   int64_t n_rows, int32_t width, int32_t self_rank, float* out_f32, void* hi, void* lo,
+                                   void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(width % 8 == 0, "hgt_halo_pull_split: row width %d must be a multiple of 8 floats", width);
+  HGT_REQUIRE(out_f32 && hi && lo, "hgt_halo_pull_split: NULL output");
+  if (n_rows == 0) return 0;
+  const int warps_per_block = 8;
+  int64_t blocks = (n_rows + warps_per_block - 1) / warps_per_block;
+  int64_t cap = (int64_t)hgt_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  k_halo_pull_split<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(
+      reinterpret_cast<const float* const*>(peer_ptrs_dev), src_rank, src_row, n_rows, width / 4, self_rank,
+      reinterpret_cast<float4*>(out_f32), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -143,13 +143,15 @@ class ShardedGraph:
             return out
         return src.index_select(0, idx32.long())
 
-    def exchange(self, x_own):
-        """[n_owned, d] owned rows -> [n_local, d] local rows in local (type-sorted) order."""
+    def exchange(self, x_own, split=False):
+        """[n_owned, d] owned rows -> [n_local, d] local rows in local (type-sorted) order.  With split=True returns
+        (x_local, (hi, lo) or None): on the p2p path the rows also come back as the bf16 hi/lo operand split and the fp32
+        copy is valid for the owned rows only."""
         if self.halo_mode in ("p2p", "auto") and x_own.is_cuda and self.world > 1:
             if self.halo_mode == "p2p":
-                return self._exchange_p2p(x_own)
+                return self._exchange_p2p(x_own, split)
             try:
-                out = self._exchange_p2p(x_own)
+                out = self._exchange_p2p(x_own, split)
                 self.halo_mode = "p2p"
                 return out
             except Exception as exc:                                   # noqa: BLE001 — both paths are GPU paths
@@ -166,9 +168,10 @@ class ShardedGraph:
         send = self._gather(x_own, self._send_idx32, self.send_idx.numel())
         if self.world > 1:
             dist.all_to_all_single(buf[self.n_owned:], send, self.recv_splits, self.send_splits, group=self.group)
-        return self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
+        res = self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
+        return (res, None) if split else res
 
-    def _exchange_p2p(self, x_own):
+    def _exchange_p2p(self, x_own, split=False):
         """Fused halo exchange: every rank publishes x_own in NVLink-mapped symmetric memory and ONE kernel pulls
         each local row (owned and halo alike) straight from its owner's HBM into type-sorted position — no send-side
         gather, no NCCL call, no re-ordering pass."""
@@ -185,15 +188,23 @@ class ShardedGraph:
         hdl.barrier(channel=1)                       # every rank's rows are published
         n_local = self.n_owned + self.n_halo
         x_local = torch.empty((n_local, d), dtype=torch.float32, device=x_own.device)
+        if split and d % 16 == 0 and d >= 64:
+            # fused pull + bf16 hi/lo conversion: halo rows never exist in fp32 on this rank
+            hi = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
+            lo = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
+            _lib.call("hgt_halo_pull_split", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(),
+                      n_local, d, self.rank, x_local.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
+            return x_local, (hi, lo)
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
                   x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        return x_local
+        return (x_local, None) if split else x_local
 
     def forward(self, conv, x_own):
         """One HGTConv layer on this rank's shard; returns the [n_owned, d] output rows (owned_global order)."""
         from .conv import HGTConv
         with HGTConv._stage("halo_exchange"):
-            x_local = self.exchange(x_own)
+            x_local, x_split = self.exchange(x_own, split=x_own.is_cuda and conv.linear_impl in (0, 2))
         if x_local.is_cuda:
             # the update epilogue writes each owned row straight to its position in owned_global order
             if getattr(self, "_out_map", None) is None:
@@ -203,7 +214,7 @@ class ShardedGraph:
             out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
                                              self.edge_time if conv.use_RTE else None, want_att=False, save=False,
                                              active_per_type=self.active_per_type, out_map=self._out_map,
-                                             out_rows=self.n_owned)
+                                             out_rows=self.n_owned, x_split=x_split)
             return out
         out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
                                          self.edge_time if conv.use_RTE else None, want_att=False, save=False,
