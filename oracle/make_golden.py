@@ -109,8 +109,51 @@ def gnn_case(name, graph, in_dim, n_hid, heads, n_layers, seed):
     print("%-28s N=%d E=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, os.path.getsize(path) / 1024))
 
 
+def synthetic_sampled_subgraph(seed, n_per_type=(40, 25, 10), n_edges=300):
+    """A sampled sub-graph in the format sample_subgraph() returns (data.py:210): feature / times per type and
+    edge_list[target_type][source_type][relation] = [[target_ser, source_ser], ...], plus a reference Graph object that
+    defines the type order and the meta graph."""
+    import numpy as np
+    data = pyg_shim.load_reference_data()
+    rng = np.random.RandomState(seed)
+    g = data.Graph()
+    names = ["paper", "author", "venue"]
+    rels = [("author", "paper", "AP_write"), ("paper", "paper", "PP_cite"), ("paper", "venue", "PV_Journal")]
+    for s_t, t_t, r in rels:                                    # defines get_meta_graph() (incl. rev_ relations)
+        g.add_edge({"type": s_t, "id": "s0"}, {"type": t_t, "id": "t0"}, time=2000, relation_type=r)
+    for t in names:
+        g.node_feature[t] = []                                  # get_types() = list(node_feature.keys())
+    feature = {t: rng.randn(n, 7).astype(np.float32) for t, n in zip(names, n_per_type)}
+    times = {t: rng.randint(1990, 2020, size=n) for t, n in zip(names, n_per_type)}
+    sizes = dict(zip(names, n_per_type))
+    from collections import defaultdict
+    edge_list = defaultdict(lambda: defaultdict(lambda: defaultdict(lambda: [])))
+    metas = g.get_meta_graph()
+    for _ in range(n_edges):
+        t_t, s_t, r = metas[rng.randint(len(metas))]
+        edge_list[t_t][s_t][r] += [[int(rng.randint(sizes[t_t])), int(rng.randint(sizes[s_t]))]]
+    for t in names:                                             # 'self' loops as in data.py:183-186
+        for i in range(sizes[t]):
+            edge_list[t][t]['self'] += [[i, i]]
+    return data, g, feature, times, edge_list
+
+
+def to_torch_case(name, seed):
+    data, g, feature, times, edge_list = synthetic_sampled_subgraph(seed)
+    ref = data.to_torch(feature, times, edge_list, g)
+    plain_edges = {t: {s: {r: [list(map(int, p)) for p in lst] for r, lst in d2.items()} for s, d2 in d1.items()}
+                   for t, d1 in edge_list.items()}
+    fx = {"feature": feature, "time": times, "edge_list": plain_edges, "types": g.get_types(),
+          "meta_graph": g.get_meta_graph(), "node_feature": ref[0], "node_type": ref[1], "edge_time": ref[2],
+          "edge_index": ref[3], "edge_type": ref[4], "node_dict": ref[5], "edge_dict": ref[6]}
+    path = os.path.join(OUT_DIR, name + ".pt")
+    torch.save(fx, path)
+    print("%-28s N=%d E=%d  %.0f KB" % (name, ref[1].numel(), ref[4].numel(), os.path.getsize(path) / 1024))
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
+    to_torch_case("to_torch", seed=31)
     c1 = synth.make_c1()
     conv_case("c1_norte", c1, 64, 4, True, False, seed=10)              # BASELINE config 1
     conv_case("c1_rte", c1, 64, 4, True, True, seed=11, grads=True)

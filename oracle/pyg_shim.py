@@ -117,6 +117,26 @@ def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "pyHGT", "conv.py"))
 
 
+def load_reference_data():
+    """Import /root/reference/pyHGT/data.py unchanged (plotting / table packages it imports at module level but never
+    uses on the to_torch path are replaced by empty stand-ins)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    install()
+    for name in ("seaborn", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "texttable", "dill"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                m = types.ModuleType(name)
+                if name == "texttable":
+                    m.Texttable = object
+                sys.modules[name] = m
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    return importlib.import_module("pyHGT.data")
+
+
 def load_reference():
     """Import /root/reference/pyHGT/{conv,model}.py unchanged; returns (conv_module, model_module)."""
     if not reference_available():

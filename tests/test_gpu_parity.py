@@ -462,3 +462,29 @@ def test_full_size_c2_properties_and_sampled_rows():
     ref, _ = hgt_oracle.hgt_forward_ref_port(params, x[nodes], g.node_type[nodes], sub_ei, g.edge_type[e_sel], None,
                                              num_types=4, num_relations=4, n_heads=H, use_norm=True, use_RTE=False)
     _close(out[sample.to(dev)], ref[local[sample]], "full-size C2: sampled destination rows vs oracle")
+
+
+def test_to_torch_device_ingest_prebuilds_plan():
+    """pyhgt_b200.data.to_torch(device=cuda, prebuild_plan=True): tensors arrive on the GPU and the layer reuses the plan."""
+    import pyhgt_b200
+    from pyhgt_b200 import data as hdata, plan as P
+    from tests.test_data_ingest import _GraphStub
+    dev = _dev()
+    fx = load_golden("to_torch")
+    g = _GraphStub(fx["types"], fx["meta_graph"])
+    P.clear_plan_cache()
+    nf, nt, etime, ei, et, node_dict, edge_dict = hdata.to_torch(fx["feature"], fx["time"], fx["edge_list"], g,
+                                                                device=dev, prebuild_plan=True)
+    assert nf.is_cuda and ei.is_cuda and torch.equal(ei.cpu(), fx["edge_index"])
+    assert len(P._CACHE) == 1
+    d = nf.shape[1]
+    torch.manual_seed(0)
+    m = pyhgt_b200.HGTConv(d, d, len(fx["types"]), len(edge_dict), 1, 0.2, True, True).to(dev).eval()
+    with torch.no_grad():
+        out = m(nf, nt, ei, et, etime)
+    assert len(P._CACHE) == 1 and torch.isfinite(out).all()       # same tensors -> cached plan reused
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref, _ = hgt_oracle.hgt_forward_ref_port(params, fx["node_feature"], fx["node_type"], fx["edge_index"],
+                                             fx["edge_type"], fx["edge_time"], num_types=len(fx["types"]),
+                                             num_relations=len(edge_dict), n_heads=1)
+    _close(out, ref, "layer on to_torch output")
