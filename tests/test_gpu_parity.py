@@ -479,12 +479,16 @@ def test_to_torch_device_ingest_prebuilds_plan():
     assert len(P._CACHE) == 1
     d = nf.shape[1]
     torch.manual_seed(0)
-    m = pyhgt_b200.HGTConv(d, d, len(fx["types"]), len(edge_dict), 1, 0.2, True, True).to(dev).eval()
+    # d = 7 is odd: the reference's RelTemporalEncoding cannot even be built for odd widths (conv.py:293-294), so the
+    # layer runs without RTE; it also exercises the scalar (VEC = 1) lane mapping and the fp32 SIMT GEMM.
+    m = pyhgt_b200.HGTConv(d, d, len(fx["types"]), len(edge_dict), 1, 0.2, True, False).to(dev).eval()
+    P.clear_plan_cache()
+    P.get_plan(nt, ei, et, None, len(fx["types"]), len(edge_dict))
     with torch.no_grad():
         out = m(nf, nt, ei, et, etime)
     assert len(P._CACHE) == 1 and torch.isfinite(out).all()       # same tensors -> cached plan reused
     params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     ref, _ = hgt_oracle.hgt_forward_ref_port(params, fx["node_feature"], fx["node_type"], fx["edge_index"],
-                                             fx["edge_type"], fx["edge_time"], num_types=len(fx["types"]),
-                                             num_relations=len(edge_dict), n_heads=1)
+                                             fx["edge_type"], None, num_types=len(fx["types"]),
+                                             num_relations=len(edge_dict), n_heads=1, use_RTE=False)
     _close(out, ref, "layer on to_torch output")
