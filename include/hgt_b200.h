@@ -212,12 +212,14 @@ int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const f
  *   type_row0 [T+2] int32 prefix of type_count;  norm_w/norm_b [T,d] or NULL;  perm NULL if identity;
  *   type_active [T] int32 or NULL: when given, only the first type_active[t] rows of type t are written
  *   (sharded runs: the remaining rows are halo sources that need no output);
- *   out [N,d] in ORIGINAL node order.
+ *   out [N,d] in ORIGINAL node order;
+ *   out_hi / out_lo [N,d] bf16 or NULL: `out` again as the bf16 hi/lo split that the NEXT layer's projection GEMM
+ *   consumes (hgt_typed_linear_presplit) — only with perm == NULL, type_active == NULL, d % 8 == 0.
  * ---------------------------------------------------------------------------------------------- */
 int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
                         const float* skip, const float* norm_w, const float* norm_b,
                         const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
-                        float* out, void* stream);
+                        float* out, void* out_hi, void* out_lo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ class HGTConv(nn.Module):
     linear_impl = 0            # 0 auto, 1 fp32 SIMT, 2 tcgen05
     event_sink = None          # bench.py: list receiving (stage, start_event, end_event) on the launch stream
     _has_skip = True           # DenseHGTConv (conv.py:143-280) has no skip gate
+    emit_split = False         # also write the output as a bf16 hi/lo split for the next layer (model.GNN sets it)
 
     def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
                  use_RTE=True, **kwargs):
@@ -201,10 +202,17 @@ class HGTConv(nn.Module):
             perm_ptr = out_map.data_ptr()
         else:
             perm_ptr = None if plan.sorted_types else plan.perm.data_ptr()
+        o_hi = o_lo = None
+        if (self.emit_split and perm_ptr is None and lt.type_active_dev is None and d % 16 == 0 and d >= 64
+                and not self.training):
+            o_hi = torch.empty((N, d), dtype=torch.bfloat16, device=o.device)
+            o_lo = torch.empty((N, d), dtype=torch.bfloat16, device=o.device)
         with self._stage("update_epilogue"):
             _lib.call("hgt_update_epilogue", o.data_ptr(), x_sorted.data_ptr(), plan.type_row0_dev.data_ptr(), T,
                       self.skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(norm_b), perm_ptr,
-                      _lib.ptr(lt.type_active_dev), N, d, out.data_ptr(), st)
+                      _lib.ptr(lt.type_active_dev), N, d, out.data_ptr(), _lib.ptr(o_hi), _lib.ptr(o_lo), st)
+        if o_hi is not None:
+            out._hgt_split = (o_hi, o_lo, out._version)          # consumed by the next layer's projection (see _core)
         return out, c["att"], (c if save else None)
 
     def _core(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
@@ -222,6 +230,11 @@ class HGTConv(nn.Module):
         lt = _plan.layer_tables(plan, d_in, d, active_per_type)
         f32 = dict(dtype=torch.float32, device=dev)
         x = node_inp.contiguous()
+        if x_split is None and plan.sorted_types and self.linear_impl in (0, 2):
+            hint = getattr(node_inp, "_hgt_split", None)            # left by the previous layer's update epilogue
+            if (hint is not None and hint[2] == node_inp._version and x is node_inp
+                    and tuple(hint[0].shape) == (N, d_in) and d_in % 16 == 0 and d_in >= 64):
+                x_split = (hint[0], hint[1])
         if plan.sorted_types:
             x_sorted = x
         else:

@@ -1,6 +1,8 @@
 // HGTConv.update epilogue (conv.py:129-133): sigmoid(skip)-gated residual + per-type LayerNorm.
 // One warp per node row; the row (d <= 1024 floats) stays in registers between the two LayerNorm passes.
 // HBM-bound: reads o and x (2*d*4 B), writes out (d*4 B) per node.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -69,13 +71,27 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
   }
 }
 
+// The next layer's projection GEMM consumes its input as a bf16 hi/lo split: emit it here instead of re-reading `out`.
+__device__ __forceinline__ void split_store(uint2* hi, uint2* lo, int64_t idx, const float4& v) {
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(f[j]);
+    l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+  }
+  hi[idx] = *reinterpret_cast<uint2*>(h);
+  lo[idx] = *reinterpret_cast<uint2*>(l);
+}
+
 // Vectorised variant: d % 4 == 0, each lane owns NV float4 chunks (chunk c = lane + 32*i), 128-bit loads/stores.
 template <int NV>
 __global__ void __launch_bounds__(256)
 k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
                       int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
                       const float* __restrict__ norm_b, const int32_t* __restrict__ perm,
-                      const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out) {
+                      const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out,
+                      uint2* __restrict__ out_hi, uint2* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
@@ -98,7 +114,10 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < nvec) orow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nvec) {
+        orow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out_hi) split_store(out_hi, out_lo, row * nvec + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
     }
     return;
   }
@@ -118,7 +137,10 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < nvec) __stcs(orow + c, y[i]);
+      if (c < nvec) {
+        __stcs(orow + c, y[i]);
+        if (out_hi) split_store(out_hi, out_lo, row * nvec + c, y[i]);
+      }
     }
     return;
   }
@@ -148,6 +170,7 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
       r.z = (y[i].z - mean) * rstd * wv.z + bv.z;
       r.w = (y[i].w - mean) * rstd * wv.w + bv.w;
       __stcs(orow + c, r);
+      if (out_hi) split_store(out_hi, out_lo, row * nvec + c, r);
     }
   }
 }
@@ -155,11 +178,11 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
 template <int NV>
 void launch_vec(const float* o, const float* x, const int32_t* type_row0, int T, const float* skip,
                 const float* norm_w, const float* norm_b, const int32_t* perm, const int32_t* type_active,
-                int64_t n_nodes, int d, float* out, cudaStream_t st) {
+                int64_t n_nodes, int d, float* out, uint2* out_hi, uint2* out_lo, cudaStream_t st) {
   const int warps_per_block = 8;
   unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
   k_update_epilogue_vec<NV><<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, T, skip, norm_w, norm_b, perm,
-                                                                  type_active, n_nodes, d, out);
+                                                                  type_active, n_nodes, d, out, out_hi, out_lo);
 }
 
 }  // namespace
@@ -167,7 +190,7 @@ void launch_vec(const float* o, const float* x, const int32_t* type_row0, int T,
 extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
                                    const float* skip, const float* norm_w, const float* norm_b,
                                    const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
-                                   float* out, void* stream_) {
+                                   float* out, void* out_hi, void* out_lo, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(d >= 1 && d <= 32 * kMaxPerLane, "hgt_update_epilogue: d=%d unsupported (max %d)", d,
               32 * kMaxPerLane);
@@ -176,12 +199,17 @@ extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t
   const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(x) |
                                         reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(norm_w) |
                                         reinterpret_cast<uintptr_t>(norm_b)) % 16 == 0);
+  HGT_REQUIRE((out_hi != nullptr) == (out_lo != nullptr), "hgt_update_epilogue: out_hi/out_lo must go together");
+  HGT_REQUIRE(out_hi == nullptr || (aligned && d % 8 == 0 && perm == nullptr && type_active == nullptr),
+              "hgt_update_epilogue: the split output needs d %% 8 == 0, 16-byte aligned buffers and identity row order");
+  uint2* hi2 = reinterpret_cast<uint2*>(out_hi);
+  uint2* lo2 = reinterpret_cast<uint2*>(out_lo);
   if (aligned && d <= 1024) {
     const int nv = (d / 4 + 31) / 32;
-    if (nv <= 1) launch_vec<1>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
-    else if (nv <= 2) launch_vec<2>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
-    else if (nv <= 4) launch_vec<4>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
-    else launch_vec<8>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, st);
+    if (nv <= 1) launch_vec<1>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else if (nv <= 2) launch_vec<2>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else if (nv <= 4) launch_vec<4>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else launch_vec<8>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
     HGT_LAUNCH_CHECK();
     return 0;
   }

@@ -33,6 +33,9 @@ class GNN(nn.Module):
         self.gcs.append(GeneralConv(conv_name, n_hid, n_hid, num_types, num_relations, n_heads, dropout,
                                     use_norm=last_norm, use_RTE=use_RTE))
         self._ptrs = {}
+        for gc in self.gcs[:-1]:                                   # every layer but the last feeds another projection
+            if isinstance(gc.base_conv, HGTConv) and type(gc.base_conv) is HGTConv:
+                gc.base_conv.emit_split = True
 
     def _adapter_cuda(self, node_feature, node_type, edge_index, edge_type, edge_time):
         conv0 = self.gcs[0].base_conv
