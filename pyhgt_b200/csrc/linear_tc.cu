@@ -6,11 +6,11 @@
 // tile: 3 tensor-core products at the bf16 rate instead of an fp32 FMA GEMM, error ~1e-5 relative —
 // far inside the 1e-3 parity bar, where a single bf16 or tf32 product would not be.
 //
-// Kernel (one CTA per 128 x BN output tile, 2 CTAs per SM so one CTA's epilogue overlaps the other's
-// main loop):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) into a STAGES-deep smem ring
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16/bf16)
-//   warps 2-5: epilogue      — tcgen05.ld 32x32b -> +bias -> st.global into the (strided) column block
+// Three kernels share the TMA / UMMA / TMEM plumbing below (all: SWIZZLE_128B K-major operands, fp32 accumulate in TMEM):
+//   k_typed_linear_tc3  (default when the column block is a multiple of 256): CTA PAIR, cta_group::2, W-stationary,
+//                       persistent; 256 x 256 pair tile, double-buffered TMEM accumulator, 8-warp transposing epilogue.
+//   k_typed_linear_tc2  same design on one CTA (n-tile = widest divisor of the column block whose resident W fits).
+//   k_typed_linear_tc   one 128 x BN tile per CTA, both operands streamed (fallback for very wide K).
 // Output tiles follow the same group / column-block tables as the SIMT kernel in linear.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
