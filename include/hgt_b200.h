@@ -221,6 +221,62 @@ int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0
                         const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
                         float* out, void* out_hi, void* out_lo, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole layer in one call (inference): HGTConv.forward, pyHGT/conv.py:56-134.
+ * Every pointer below is a DEVICE pointer except the h_* tables (host copies of the typed-linear group tables, used
+ * only to size grids).  Parameter pointer tables (wq ... norm_b) are device arrays of num_types device pointers, one
+ * per nn.Linear / nn.LayerNorm of the module (conv.py:34-40).  The plan arrays come from hgt_plan_*; the typed-linear
+ * tables are the ones hgt_typed_linear takes (projection: Q + [K'|V'] blocks; rte: K'R/V'R tables; rt: the single
+ * 240 x d group of RelTemporalEncoding.lin; upd: a_linears).  Nothing is allocated or synchronised.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  /* sizes and switches */
+  int64_t n_nodes, n_edges, kv_rows, cat_rows, q_off, kv_off, proj_elems;
+  int32_t num_types, num_relations, n_heads, d_in, d_out, n_pairs;
+  int32_t use_rte, use_norm, edge_variant, linear_impl;
+  int32_t n_tiles, n_split, n_hubs;
+  int32_t n_proj_groups, n_rte_groups, n_upd_groups;
+  /* plan (hgt_plan_*) */
+  const int32_t* perm;        /* NULL when node_type is already sorted */
+  const int32_t* type_row0;   /* [T+2] */
+  const int32_t* type_active; /* [T] or NULL (sharded runs) */
+  const int32_t* out_map;     /* [N] or NULL: rank-order row -> output row (sharded runs) */
+  const int32_t* row_ptr;
+  const int32_t* kv_row;
+  const int32_t* rte_row;     /* NULL when !use_rte */
+  const int32_t* csr_eid;
+  const int32_t* tiles;
+  const int32_t* hubs;
+  const int32_t* pair_type;
+  const int32_t* pair_rel;
+  const int32_t* cat_row0;
+  const int32_t* q_row0;
+  /* typed-linear tables */
+  const hgt_lin_group* proj_groups; const hgt_lin_group* h_proj_groups; const hgt_lin_cblock* proj_cblocks;
+  const hgt_lin_group* rte_groups;  const hgt_lin_group* h_rte_groups;  const hgt_lin_cblock* rte_cblocks;
+  const hgt_lin_group* rt_groups;   const hgt_lin_group* h_rt_groups;   const hgt_lin_cblock* rt_cblocks;
+  const hgt_lin_group* upd_groups;  const hgt_lin_group* h_upd_groups;  const hgt_lin_cblock* upd_cblocks;
+  /* parameters */
+  const float* const* wq; const float* const* bq;
+  const float* const* wk; const float* const* bk;
+  const float* const* wv; const float* const* bv;
+  const float* const* wa; const float* const* ba;
+  const float* const* norm_w; const float* const* norm_b;   /* NULL when !use_norm */
+  const float* relation_att; const float* relation_msg; const float* relation_pri; const float* skip;
+  const float* emb_weight; const float* emb_lin_w; const float* emb_lin_b;   /* NULL when !use_rte */
+  /* data */
+  const float* x;             /* [N, d_in] in original node order */
+  const void* x_hi; const void* x_lo;   /* optional: x already split to bf16 hi/lo (rank order == original order) */
+  float* out;                 /* [N or out rows, d_out] */
+  float* att;                 /* [E, H] or NULL */
+  void* out_hi; void* out_lo; /* optional: out again as the bf16 hi/lo split for the next layer */
+} hgt_conv_args;
+
+uint64_t hgt_conv_args_size(void);   /* sizeof(hgt_conv_args): lets a foreign-language binding check its struct layout */
+int hgt_conv_workspace_bytes(const hgt_conv_args* args, size_t* out_bytes);
+int hgt_conv_forward(const hgt_conv_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,8 +39,27 @@ SIGNATURES = {
     "hgt_typed_linear_presplit_workspace_bytes": [_p, _i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_typed_linear_presplit": [_p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p],
     "hgt_edge_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _sz, _p],
+    "hgt_conv_workspace_bytes": [_p, _c.POINTER(_sz)],
+    "hgt_conv_forward": [_p, _p, _sz, _p],
     "hgt_update_epilogue": [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p],
 }
+
+class ConvArgs(ctypes.Structure):
+    """Mirror of `hgt_conv_args` (include/hgt_b200.h); field order and types must match the C struct exactly
+    (checked against hgt_conv_args_size() in tests/test_capi.py)."""
+    _I64 = ["n_nodes", "n_edges", "kv_rows", "cat_rows", "q_off", "kv_off", "proj_elems"]
+    _I32 = ["num_types", "num_relations", "n_heads", "d_in", "d_out", "n_pairs", "use_rte", "use_norm", "edge_variant",
+            "linear_impl", "n_tiles", "n_split", "n_hubs", "n_proj_groups", "n_rte_groups", "n_upd_groups"]
+    _PTR = ["perm", "type_row0", "type_active", "out_map", "row_ptr", "kv_row", "rte_row", "csr_eid", "tiles", "hubs",
+            "pair_type", "pair_rel", "cat_row0", "q_row0",
+            "proj_groups", "h_proj_groups", "proj_cblocks", "rte_groups", "h_rte_groups", "rte_cblocks",
+            "rt_groups", "h_rt_groups", "rt_cblocks", "upd_groups", "h_upd_groups", "upd_cblocks",
+            "wq", "bq", "wk", "bk", "wv", "bv", "wa", "ba", "norm_w", "norm_b",
+            "relation_att", "relation_msg", "relation_pri", "skip", "emb_weight", "emb_lin_w", "emb_lin_b",
+            "x", "x_hi", "x_lo", "out", "att", "out_hi", "out_lo"]
+    _fields_ = ([(n, ctypes.c_int64) for n in _I64] + [(n, ctypes.c_int32) for n in _I32] +
+                [(n, ctypes.c_void_p) for n in _PTR])
+
 
 LIN_GROUP_DTYPE = np.dtype([("a_row0", "<i8"), ("m", "<i8"), ("w_row0", "<i4"), ("n_cblocks", "<i4"),
                             ("cb_first", "<i4"), ("has_bias", "<i4")])
@@ -71,6 +90,8 @@ def load():
         fn.argtypes = args
     lib.hgt_kernel_launches.restype = _c.c_uint64
     lib.hgt_kernel_launches.argtypes = []
+    lib.hgt_conv_args_size.restype = _c.c_uint64
+    lib.hgt_conv_args_size.argtypes = []
     _lib = lib
     return lib
 

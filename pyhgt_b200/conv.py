@@ -81,6 +81,7 @@ class HGTConv(nn.Module):
     event_sink = None          # bench.py: list receiving (stage, start_event, end_event) on the launch stream
     _has_skip = True           # DenseHGTConv (conv.py:143-280) has no skip gate
     emit_split = False         # also write the output as a bf16 hi/lo split for the next layer (model.GNN sets it)
+    fused_call = True          # inference goes through ONE C-ABI call (hgt_conv_forward) instead of ~12
 
     def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
                  use_RTE=True, **kwargs):
@@ -183,10 +184,104 @@ class HGTConv(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------
+    def _forward_fused(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att,
+                       active_per_type=None, out_map=None, out_rows=None, x_split=None):
+        """Inference through the single entry point hgt_conv_forward (csrc/layer.cu).  The argument block is cached per
+        (plan tables, parameter locations); per call only the data pointers change."""
+        dev = node_inp.device
+        d_in, d, H, T, R = self.in_dim, self.out_dim, self.n_heads, self.num_types, self.num_relations
+        plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if self.use_RTE else None, T, R)
+        N, E = plan.n_nodes, plan.n_edges
+        if node_inp.shape[0] != N:
+            raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
+        lt = _plan.layer_tables(plan, d_in, d, active_per_type)
+        tabs = [self._ptrs("wq", [l.weight for l in self.q_linears], dev),
+                self._ptrs("bq", [l.bias for l in self.q_linears], dev),
+                self._ptrs("wk", [l.weight for l in self.k_linears], dev),
+                self._ptrs("bk", [l.bias for l in self.k_linears], dev),
+                self._ptrs("wv", [l.weight for l in self.v_linears], dev),
+                self._ptrs("bv", [l.bias for l in self.v_linears], dev),
+                self._ptrs("wa", [l.weight for l in self.a_linears], dev),
+                self._ptrs("ba", [l.bias for l in self.a_linears], dev)]
+        if self.use_norm:
+            tabs += [self._ptrs("nw", [n.weight for n in self.norms], dev), self._ptrs("nb", [n.bias for n in self.norms], dev)]
+        scalars = [self.relation_att, self.relation_msg, self.relation_pri, self.skip]
+        if self.use_RTE:
+            scalars += [self.emb.emb.weight, self.emb.lin.weight, self.emb.lin.bias]
+        key = (id(lt),) + tuple(t.data_ptr() for t in tabs) + tuple(t.data_ptr() for t in scalars)
+        cache = self.__dict__.setdefault("_args_cache", {})
+        ent = cache.get(key)
+        if ent is None:
+            a = _lib.ConvArgs()
+            a.n_nodes, a.n_edges, a.kv_rows, a.cat_rows = N, E, plan.kv_rows, lt.cat_rows
+            a.q_off, a.kv_off, a.proj_elems = lt.q_off, lt.kv_off, lt.proj_elems
+            a.num_types, a.num_relations, a.n_heads, a.d_in, a.d_out, a.n_pairs = T, R, H, d_in, d, plan.n_pairs
+            a.use_rte, a.use_norm = int(self.use_RTE), int(self.use_norm)
+            a.n_tiles, a.n_split, a.n_hubs = plan.n_tiles, plan.n_split, plan.n_hubs
+            a.perm = None if plan.sorted_types else plan.perm.data_ptr()
+            a.type_row0 = plan.type_row0_dev.data_ptr()
+            a.type_active = _lib.ptr(lt.type_active_dev)
+            a.row_ptr, a.kv_row = plan.row_ptr.data_ptr(), plan.kv_row.data_ptr()
+            a.rte_row = plan.rte_row.data_ptr() if self.use_RTE else None
+            a.csr_eid, a.tiles, a.hubs = plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.hubs.data_ptr()
+            a.pair_type, a.pair_rel = plan.pair_type_dev.data_ptr(), plan.pair_rel_dev.data_ptr()
+            a.cat_row0, a.q_row0 = lt.cat_row0_dev.data_ptr(), lt.q_row0_dev.data_ptr()
+            for name, tab in (("proj", lt.proj_groups), ("rte", lt.rte_groups), ("rt", lt.rt_group), ("upd", lt.upd_groups)):
+                g_dev, g_host, n_g, c_dev = tab
+                setattr(a, name + "_groups", g_dev.data_ptr())
+                setattr(a, "h_" + name + "_groups", g_host.ctypes.data)
+                setattr(a, name + "_cblocks", c_dev.data_ptr())
+                if name != "rt":
+                    setattr(a, "n_" + name + "_groups", n_g)
+            (a.wq, a.bq, a.wk, a.bk, a.wv, a.bv, a.wa, a.ba) = [t.data_ptr() for t in tabs[:8]]
+            if self.use_norm:
+                a.norm_w, a.norm_b = tabs[8].data_ptr(), tabs[9].data_ptr()
+            a.relation_att, a.relation_msg = self.relation_att.data_ptr(), self.relation_msg.data_ptr()
+            a.relation_pri, a.skip = self.relation_pri.data_ptr(), self.skip.data_ptr()
+            if self.use_RTE:
+                a.emb_weight, a.emb_lin_w = self.emb.emb.weight.data_ptr(), self.emb.lin.weight.data_ptr()
+                a.emb_lin_b = self.emb.lin.bias.data_ptr()
+            if len(cache) >= 4:                                    # entries pin their plan: keep only a few
+                cache.clear()
+            ent = cache[key] = (a, lt, plan, tabs)                 # keep the tables the pointers refer to alive
+        a = ent[0]
+        x = node_inp.contiguous()
+        if x_split is None and plan.sorted_types and self.linear_impl in (0, 2):
+            hint = getattr(node_inp, "_hgt_split", None)
+            if (hint is not None and hint[2] == node_inp._version and x is node_inp
+                    and tuple(hint[0].shape) == (N, d_in) and d_in % 16 == 0 and d_in >= 64):
+                x_split = (hint[0], hint[1])
+        a.edge_variant, a.linear_impl = self.edge_variant, self.linear_impl
+        a.x = x.data_ptr()
+        a.x_hi, a.x_lo = (x_split[0].data_ptr(), x_split[1].data_ptr()) if x_split is not None else (None, None)
+        if out_map is not None and not plan.sorted_types:
+            raise ValueError("out_map needs a type-sorted node order")
+        a.out_map = _lib.ptr(out_map)
+        out = torch.empty((N if out_rows is None else out_rows, d), dtype=torch.float32, device=dev)
+        att = torch.empty((E, H), dtype=torch.float32, device=dev) if want_att else None
+        a.out, a.att = out.data_ptr(), _lib.ptr(att)
+        o_hi = o_lo = None
+        if (self.emit_split and plan.sorted_types and out_map is None and lt.type_active_dev is None and d % 16 == 0
+                and d >= 64):
+            o_hi = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
+            o_lo = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
+        a.out_hi, a.out_lo = _lib.ptr(o_hi), _lib.ptr(o_lo)
+        wsb = ctypes.c_size_t()
+        _lib.call("hgt_conv_workspace_bytes", ctypes.byref(a), ctypes.byref(wsb))
+        ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
+        _lib.call("hgt_conv_forward", ctypes.byref(a), ws.data_ptr(), ws.numel(), _stream())
+        if o_hi is not None:
+            out._hgt_split = (o_hi, o_lo, out._version)
+        return out, att, None
+
     def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
                       active_per_type=None, out_map=None, out_rows=None, x_split=None):
         """out_map / out_rows (sharded runs): int32 [N] map from rank-order row to output row and the number of output
         rows; rows that are not active (halo sources) are never written, so the output holds exactly the owned rows."""
+        if (self.fused_call and not save and HGTConv.event_sink is None and type(self)._has_skip
+                and not (self.training and self.drop.p > 0)):
+            return self._forward_fused(node_inp, node_type, edge_index, edge_type, edge_time, want_att,
+                                       active_per_type, out_map, out_rows, x_split)
         c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
                        gelu_before_a=True, x_split=x_split)
         plan, lt, o, x_sorted, N, d, T, st = c["plan"], c["lt"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]

@@ -12,7 +12,8 @@ constexpr int kMaxPerLane = 32;   // d <= 1024
 __global__ void __launch_bounds__(256)
 k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
                   int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
-                  const float* __restrict__ norm_b, const int32_t* __restrict__ perm,
+                  const float* __restrict__ norm_b, const float* const* __restrict__ norm_wp,
+                  const float* const* __restrict__ norm_bp, const int32_t* __restrict__ perm,
                   const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -41,7 +42,7 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
       y[i] = 0.f;
     }
   }
-  if (norm_w == nullptr) {
+  if (norm_w == nullptr && norm_wp == nullptr) {
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; ++i) {
       int c = lane + i * 32;
@@ -62,8 +63,8 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
   }
   for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
   const float rstd = rsqrtf(var / d + 1e-5f);              // nn.LayerNorm eps (conv.py:40)
-  const float* w = norm_w + (int64_t)t * d;
-  const float* b = norm_b + (int64_t)t * d;
+  const float* w = norm_wp ? norm_wp[t] : norm_w + (int64_t)t * d;
+  const float* b = norm_bp ? norm_bp[t] : norm_b + (int64_t)t * d;
 #pragma unroll
   for (int i = 0; i < kMaxPerLane; ++i) {
     int c = lane + i * 32;
@@ -89,7 +90,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, const int32_t* __restrict__ type_row0,
                       int T, const float* __restrict__ skip, const float* __restrict__ norm_w,
-                      const float* __restrict__ norm_b, const int32_t* __restrict__ perm,
+                      const float* __restrict__ norm_b, const float* const* __restrict__ norm_wp,
+                      const float* const* __restrict__ norm_bp, const int32_t* __restrict__ perm,
                       const int32_t* __restrict__ type_active, int64_t n_nodes, int d, float* __restrict__ out,
                       uint2* __restrict__ out_hi, uint2* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
@@ -133,7 +135,7 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
     y[i].w = ov[i].w * alpha + xv[i].w * beta;
     sum += (y[i].x + y[i].y) + (y[i].z + y[i].w);
   }
-  if (norm_w == nullptr) {
+  if (norm_w == nullptr && norm_wp == nullptr) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
@@ -157,8 +159,8 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
   }
   for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
   const float rstd = rsqrtf(var / d + 1e-5f);
-  const float4* w = reinterpret_cast<const float4*>(norm_w + (int64_t)t * d);
-  const float4* b = reinterpret_cast<const float4*>(norm_b + (int64_t)t * d);
+  const float4* w = reinterpret_cast<const float4*>(norm_wp ? norm_wp[t] : norm_w + (int64_t)t * d);
+  const float4* b = reinterpret_cast<const float4*>(norm_bp ? norm_bp[t] : norm_b + (int64_t)t * d);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
@@ -177,25 +179,28 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
 
 template <int NV>
 void launch_vec(const float* o, const float* x, const int32_t* type_row0, int T, const float* skip,
-                const float* norm_w, const float* norm_b, const int32_t* perm, const int32_t* type_active,
-                int64_t n_nodes, int d, float* out, uint2* out_hi, uint2* out_lo, cudaStream_t st) {
+                const float* norm_w, const float* norm_b, const float* const* norm_wp, const float* const* norm_bp,
+                const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int d, float* out, uint2* out_hi,
+                uint2* out_lo, cudaStream_t st) {
   const int warps_per_block = 8;
   unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
-  k_update_epilogue_vec<NV><<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, T, skip, norm_w, norm_b, perm,
-                                                                  type_active, n_nodes, d, out, out_hi, out_lo);
+  k_update_epilogue_vec<NV><<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, T, skip, norm_w, norm_b, norm_wp,
+                                                                  norm_bp, perm, type_active, n_nodes, d, out, out_hi,
+                                                                  out_lo);
 }
 
 }  // namespace
 
-extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
-                                   const float* skip, const float* norm_w, const float* norm_b,
-                                   const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
-                                   float* out, void* out_hi, void* out_lo, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+int hgt_update_epilogue_impl(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
+                             const float* skip, const float* norm_w, const float* norm_b, const float* const* norm_wp,
+                             const float* const* norm_bp, const int32_t* perm, const int32_t* type_active,
+                             int64_t n_nodes, int32_t d, float* out, void* out_hi, void* out_lo, cudaStream_t st) {
   HGT_REQUIRE(d >= 1 && d <= 32 * kMaxPerLane, "hgt_update_epilogue: d=%d unsupported (max %d)", d,
               32 * kMaxPerLane);
-  HGT_REQUIRE((norm_w == nullptr) == (norm_b == nullptr), "hgt_update_epilogue: norm_w/norm_b must go together");
+  HGT_REQUIRE((norm_w == nullptr) == (norm_b == nullptr) && (norm_wp == nullptr) == (norm_bp == nullptr),
+              "hgt_update_epilogue: LayerNorm weight and bias must go together");
   if (n_nodes == 0) return 0;
+  // with pointer tables the per-type vectors are separate nn.LayerNorm parameters: torch allocations, 16-byte aligned
   const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(x) |
                                         reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(norm_w) |
                                         reinterpret_cast<uintptr_t>(norm_b)) % 16 == 0);
@@ -206,17 +211,25 @@ extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t
   uint2* lo2 = reinterpret_cast<uint2*>(out_lo);
   if (aligned && d <= 1024) {
     const int nv = (d / 4 + 31) / 32;
-    if (nv <= 1) launch_vec<1>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
-    else if (nv <= 2) launch_vec<2>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
-    else if (nv <= 4) launch_vec<4>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
-    else launch_vec<8>(o, x, type_row0, num_types, skip, norm_w, norm_b, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    if (nv <= 1) launch_vec<1>(o, x, type_row0, num_types, skip, norm_w, norm_b, norm_wp, norm_bp, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else if (nv <= 2) launch_vec<2>(o, x, type_row0, num_types, skip, norm_w, norm_b, norm_wp, norm_bp, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else if (nv <= 4) launch_vec<4>(o, x, type_row0, num_types, skip, norm_w, norm_b, norm_wp, norm_bp, perm, type_active, n_nodes, d, out, hi2, lo2, st);
+    else launch_vec<8>(o, x, type_row0, num_types, skip, norm_w, norm_b, norm_wp, norm_bp, perm, type_active, n_nodes, d, out, hi2, lo2, st);
     HGT_LAUNCH_CHECK();
     return 0;
   }
   const int warps_per_block = 8;
   unsigned grid = (unsigned)((n_nodes + warps_per_block - 1) / warps_per_block);
-  k_update_epilogue<<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, num_types, skip, norm_w, norm_b,
-                                                           perm, type_active, n_nodes, d, out);
+  k_update_epilogue<<<grid, warps_per_block * 32, 0, st>>>(o, x, type_row0, num_types, skip, norm_w, norm_b, norm_wp,
+                                                           norm_bp, perm, type_active, n_nodes, d, out);
   HGT_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int hgt_update_epilogue(const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
+                                   const float* skip, const float* norm_w, const float* norm_b,
+                                   const int32_t* perm, const int32_t* type_active, int64_t n_nodes, int32_t d,
+                                   float* out, void* out_hi, void* out_lo, void* stream_) {
+  return hgt_update_epilogue_impl(o, x, type_row0, num_types, skip, norm_w, norm_b, nullptr, nullptr, perm,
+                                  type_active, n_nodes, d, out, out_hi, out_lo, (cudaStream_t)stream_);
 }

@@ -35,7 +35,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_ctypes_signatures_cover_the_header():
     from pyhgt_b200 import _lib
-    declared = set(_declared_symbols()) - {"hgt_last_error", "hgt_kernel_launches"}
+    declared = set(_declared_symbols()) - {"hgt_last_error", "hgt_kernel_launches", "hgt_conv_args_size"}
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
 
 
@@ -58,3 +58,22 @@ def test_no_cpu_fallback():
     with torch.no_grad(), pytest.raises(_lib.HgtError):
         m(torch.randn(3, 16), torch.zeros(3, dtype=torch.long), torch.zeros(2, 1, dtype=torch.long),
           torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+
+
+def test_conv_args_struct_layout_matches_c():
+    """The ctypes mirror of hgt_conv_args has the C struct's size, and its field list follows the header's order."""
+    from pyhgt_b200 import _lib
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.ConvArgs) == lib.hgt_conv_args_size()
+    text = open(os.path.join(ROOT, "include", "hgt_b200.h")).read()
+    body = text[text.index("typedef struct {", text.index("Whole layer in one call")):text.index("} hgt_conv_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).replace("typedef struct {", "")
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        parts = [p_.strip() for p_ in decl.split(",")]
+        names.append(parts[0].split()[-1].lstrip("*"))
+        names += [p_.lstrip("*").strip() for p_ in parts[1:]]
+    assert names == [f[0] for f in _lib.ConvArgs._fields_], names

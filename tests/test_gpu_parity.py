@@ -44,16 +44,19 @@ def _run(m, fx, dev, key="node_inp"):
     return out
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("name", CONV_FIXTURES)
-def test_forward_matches_reference_golden(name, variant):
+def test_forward_matches_reference_golden(name, variant, fused):
+    """fused=True: the whole layer through ONE C-ABI call (hgt_conv_forward); False: the per-stage entry points."""
     dev = _dev()
     fx = load_golden(name)
     m = _module_from_fixture(fx, dev)
     m.edge_variant = variant
+    m.fused_call = fused
     out = _run(m, fx, dev)
-    _close(out, fx["out"], "%s out (variant %d)" % (name, variant))
-    _close(m.att, fx["att"], "%s att (variant %d)" % (name, variant), atol=1e-4)
+    _close(out, fx["out"], "%s out (variant %d, fused %s)" % (name, variant, fused))
+    _close(m.att, fx["att"], "%s att (variant %d, fused %s)" % (name, variant, fused), atol=1e-4)
 
 
 def test_four_argument_forward_without_rte():
