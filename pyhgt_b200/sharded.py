@@ -38,6 +38,32 @@ def partition_owner(node_type, edge_index, num_types, world):
     return owner
 
 
+class _HaloExchange(torch.autograd.Function):
+    """Differentiable halo exchange (NCCL / gloo path).  forward: owned rows -> local rows [per type: owned | halo].
+    backward: the gradient of every halo row goes back to its owner with the REVERSE all-to-all and is added to the
+    owner's row (a source feeds edges on several ranks), the gradient of owned rows stays local."""
+
+    @staticmethod
+    def forward(ctx, x_own, shard):
+        ctx.shard = shard
+        return shard._exchange_nccl(x_own)
+
+    @staticmethod
+    def backward(ctx, dx_local):
+        sh = ctx.shard
+        d = dx_local.shape[1]
+        dx_local = dx_local.contiguous()
+        d_cat = torch.empty_like(dx_local)
+        d_cat.index_copy_(0, sh.cat_index.long(), dx_local)              # undo the [x_own | recv] -> local re-ordering
+        d_own = d_cat[:sh.n_owned].clone()
+        d_recv = d_cat[sh.n_owned:].contiguous()
+        d_send = torch.empty((sh.send_idx.numel(), d), dtype=dx_local.dtype, device=dx_local.device)
+        if sh.world > 1:
+            dist.all_to_all_single(d_send, d_recv, sh.send_splits, sh.recv_splits, group=sh.group)
+        d_own.index_add_(0, sh.send_idx, d_send)
+        return d_own, None
+
+
 @dataclass
 class ShardedGraph:
     rank: int
@@ -160,6 +186,10 @@ class ShardedGraph:
                 self.halo_mode = "nccl"
         elif self.halo_mode == "auto":
             self.halo_mode = "nccl"
+        res = self._exchange_nccl(x_own)
+        return (res, None) if split else res
+
+    def _exchange_nccl(self, x_own):
         d = x_own.shape[1]
         if getattr(self, "_send_idx32", None) is None:
             self._send_idx32 = self.send_idx.to(torch.int32)
@@ -168,8 +198,7 @@ class ShardedGraph:
         send = self._gather(x_own, self._send_idx32, self.send_idx.numel())
         if self.world > 1:
             dist.all_to_all_single(buf[self.n_owned:], send, self.recv_splits, self.send_splits, group=self.group)
-        res = self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
-        return (res, None) if split else res
+        return self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
 
     def _exchange_p2p(self, x_own, split=False):
         """Fused halo exchange: every rank publishes x_own in NVLink-mapped symmetric memory and ONE kernel pulls
@@ -199,6 +228,20 @@ class ShardedGraph:
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
                   x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return (x_local, None) if split else x_local
+
+    def forward_train(self, conv, x_own):
+        """Differentiable sharded layer (BASELINE config 4): halo exchange with a reverse all-to-all in backward, the
+        layer's autograd path on the local graph, owned rows out.  Parameter gradients are PARTIAL per rank (each rank
+        sees only its destinations): sum them with `allreduce_grads` (or wrap the model in DistributedDataParallel)."""
+        x_local = _HaloExchange.apply(x_own, self)
+        out = conv(x_local, self.node_type, self.edge_index, self.edge_type, self.edge_time if conv.use_RTE else None)
+        return out.index_select(0, self.own_rows)
+
+    def allreduce_grads(self, module):
+        if self.world > 1:
+            for p in module.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, group=self.group)
 
     def forward(self, conv, x_own):
         """One HGTConv layer on this rank's shard; returns the [n_owned, d] output rows (owned_global order)."""
