@@ -31,7 +31,9 @@ if ROOT not in sys.path:
 METRIC = "HGTConv fwd edges/sec"
 UNIT = "edges/s"
 D, HEADS, TYPES, RELS = 256, 8, 4, 4
-CPU_SAMPLE_SCALE = 0.05          # ogbn-mag-shaped x0.05: ~1.06 M edges (the reference needs ~6 GB per 1 M edges)
+# ogbn-mag-shaped x0.05: ~1.06 M edges (the reference needs ~6 GB per 1 M edges); HGT_BENCH_CPU_SCALE shrinks it (tests)
+CPU_SAMPLE_SCALE = float(os.environ.get("HGT_BENCH_CPU_SCALE", "0.05"))
+CPU_PROBE_SCALE = min(0.01, CPU_SAMPLE_SCALE)
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -107,7 +109,7 @@ def run_cpu_port(steps, warmup, scale=CPU_SAMPLE_SCALE):
     cores = os.cpu_count() or 1
     # "all the host threads it can use": the reference's small eager ops slow down when oversubscribed, so pick
     # the thread count with the best throughput on a x0.01 probe and time the sample with that.
-    probe = synth.make_mag_shaped(0.01)
+    probe = synth.make_mag_shaped(CPU_PROBE_SCALE)
     pp = hgt_oracle.init_params(D, D, TYPES, RELS, HEADS, use_norm=True, use_RTE=False, seed=0)
     px = torch.randn(probe.num_nodes, D, generator=torch.Generator().manual_seed(0))
     best_t, best_dt = cores, float("inf")
@@ -127,7 +129,7 @@ def run_cpu_port(steps, warmup, scale=CPU_SAMPLE_SCALE):
     torch.set_num_threads(best_t)
     # bound the sample to ~5 s per forward (about 15-25 s of CPU work in total): edges/s is ~scale-invariant
     probe_eps = probe.num_edges / best_dt
-    scale = max(0.01, min(scale, 5.0 * probe_eps / 21_111_007))
+    scale = max(min(0.01, scale), min(scale, 5.0 * probe_eps / 21_111_007))
     g = synth.make_mag_shaped(scale)
     params = hgt_oracle.init_params(D, D, TYPES, RELS, HEADS, use_norm=True, use_RTE=False, seed=0)
     x = torch.randn(g.num_nodes, D, generator=torch.Generator().manual_seed(0))
