@@ -70,3 +70,42 @@ def test_golden_reproducible_from_reference():
         out = m(fx["node_inp"], fx["node_type"], fx["edge_index"], fx["edge_type"], fx["edge_time"])
     assert torch.allclose(out, fx["out"], rtol=1e-6, atol=1e-6)
     assert torch.allclose(m.att, fx["att"], rtol=1e-6, atol=1e-7)
+
+
+def _random_case(seed, n=120, e=900, T=3, R=4, d=16, H=4, rte=True):
+    from pyhgt_b200 import synth
+    g = synth.make_random(n, e, T, R, seed=seed, isolated_frac=0.2, self_loops=10, duplicate_edges=20)
+    params = hgt_oracle.init_params(d, d, T, R, H, use_norm=True, use_RTE=rte, seed=seed + 1)
+    gen = torch.Generator().manual_seed(seed + 2)
+    for k in list(params):                                  # move the constant inits (skip, pri, LayerNorm) off 1 / 0
+        if k in ("skip", "relation_pri") or k.startswith("norms"):
+            params[k] = params[k] + 0.3 * torch.randn(params[k].shape, generator=gen)
+    x = torch.randn(g.num_nodes, d, generator=gen)
+    kw = dict(num_types=T, num_relations=R, n_heads=H, use_norm=True, use_RTE=rte)
+    return g, params, x, kw
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_port_and_dense_fp64_agree_on_random_graphs(seed):
+    """The two independent restatements (per-triple fp32 port, node-level fp64) agree beyond the fixtures."""
+    g, params, x, kw = _random_case(seed, rte=bool(seed % 2))
+    o1, a1 = hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index, g.edge_type, g.edge_time, **kw)
+    o2, a2 = hgt_oracle.hgt_forward_dense_fp64(params, x, g.node_type, g.edge_index, g.edge_type, g.edge_time, **kw)
+    assert torch.allclose(o1, o2.float(), rtol=2e-4, atol=2e-4)
+    assert torch.allclose(a1, a2.float(), rtol=2e-4, atol=1e-5)
+
+
+def test_oracle_invariances():
+    """Permuting the edge list permutes att and leaves out unchanged; relabelling the nodes permutes out rows."""
+    g, params, x, kw = _random_case(7)
+    out, att = hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index, g.edge_type, g.edge_time, **kw)
+    gen = torch.Generator().manual_seed(0)
+    pe = torch.randperm(g.num_edges, generator=gen)
+    out2, att2 = hgt_oracle.hgt_forward_ref_port(params, x, g.node_type, g.edge_index[:, pe], g.edge_type[pe],
+                                                 g.edge_time[pe], **kw)
+    assert torch.allclose(out2, out, atol=1e-5) and torch.allclose(att2, att[pe], atol=1e-6)
+    pn = torch.randperm(g.num_nodes, generator=gen)        # new id of old node i is inv[i]
+    inv = torch.empty_like(pn); inv[pn] = torch.arange(g.num_nodes)
+    out3, _ = hgt_oracle.hgt_forward_ref_port(params, x[pn], g.node_type[pn], inv[g.edge_index], g.edge_type,
+                                              g.edge_time, **kw)
+    assert torch.allclose(out3, out[pn], atol=1e-5)
