@@ -13,6 +13,7 @@ Plans are cached per (node_type, edge_index, edge_type, edge_time) tensor identi
 GNN stack (pyHGT/model.py:78-79 passes the same tensors to every layer) share one plan.
 """
 import ctypes
+import os
 import weakref
 from dataclasses import dataclass, field
 
@@ -22,9 +23,8 @@ import torch
 from . import _lib
 
 RTE_MAX_LEN = 240            # conv.py:287
-import os as _os
-TILE_TARGET_EDGES = int(_os.environ.get("HGT_TILE_EDGES", "64"))      # edges per work tile (cost units: csrc/plan.cu)
-TILE_SPLIT_EDGES = int(_os.environ.get("HGT_SPLIT_EDGES", "1024"))    # larger destinations are split across warps
+TILE_TARGET_EDGES = int(os.environ.get("HGT_TILE_EDGES", "64"))       # edges per work tile (cost units: csrc/plan.cu)
+TILE_SPLIT_EDGES = int(os.environ.get("HGT_SPLIT_EDGES", "1024"))     # larger destinations are split across warps
 
 
 def _stream():

@@ -75,7 +75,7 @@ def _zipf_ids(gen, n_ids, count, alpha):
     return mix
 
 
-def _assemble(blocks, counts, T, R, gen, name, shuffle_within_block=False):
+def _assemble(blocks, counts, T, R, gen, name):
     node_type, _ = _type_layout(counts)
     src = torch.cat([b[0] for b in blocks]) if blocks else torch.zeros(0, dtype=torch.int64)
     dst = torch.cat([b[1] for b in blocks]) if blocks else torch.zeros(0, dtype=torch.int64)
