@@ -68,9 +68,6 @@ class _EdgeAttention(torch.autograd.Function):
         return dq, dkv, dkvr, None, None, None, None
 
 
-_CBLOCKS_HOST = {}
-
-
 class _TypedLinear(torch.autograd.Function):
     """Grouped typed linear through the C ABI (``hgt_typed_linear``: tcgen05 split-bf16 when the shape allows).
     forward : out_flat[cblock c of group g][m, :] = A[rows_g] @ W_cat[rows of (g, c)]^T + b_cat
@@ -85,10 +82,7 @@ class _TypedLinear(torch.autograd.Function):
         out = torch.zeros(out_elems, dtype=torch.float32, device=a.device)
         module._typed_linear(a, a.shape[1], w_cat, b_cat, a.shape[1], width, table, out, impl, _stream())
         ctx.table, ctx.width, ctx.has_bias = table, width, b_cat is not None
-        key = (c_dev.data_ptr(), c_dev.numel())
-        if key not in _CBLOCKS_HOST:                                  # column-block table on the host (once per table)
-            _CBLOCKS_HOST[key] = np.frombuffer(c_dev.cpu().numpy().tobytes(), dtype=_lib.LIN_CBLOCK_DTYPE)
-        ctx.cblocks_host = _CBLOCKS_HOST[key]
+        ctx.cblocks_host = table.c_host                                # host copy kept with the table (plan._pack_groups)
         ctx.save_for_backward(a, w_cat)
         return out
 

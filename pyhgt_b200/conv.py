@@ -126,6 +126,15 @@ class HGTConv(nn.Module):
         return '{}(in_dim={}, out_dim={}, num_types={}, num_types={})'.format(
             self.__class__.__name__, self.in_dim, self.out_dim, self.num_types, self.num_relations)
 
+    def __getstate__(self):
+        """Launch caches (ctypes argument blocks, device pointer tables, pinned plans) are per-process state: they are
+        dropped from the pickled / deep-copied module so `torch.save(model)` (OAG/train_paper_field.py:279) works after
+        a forward; they are rebuilt lazily."""
+        state = self.__dict__.copy()
+        state.pop("_args_cache", None)
+        state["_ptr_tables"] = {}
+        return state
+
     # ------------------------------------------------------------------------------------------
     def _ptrs(self, name, tensors, device):
         tab = self._ptr_tables.get(name)

@@ -216,10 +216,20 @@ extern "C" int hgt_typed_linear(const float* A, int64_t lda, const float* W, con
                                 int32_t n_groups, const hgt_lin_cblock* cblocks, float* out, int32_t impl,
                                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  HGT_REQUIRE(n_groups >= 0 && n_groups <= kMaxGroups, "hgt_typed_linear: n_groups=%d exceeds %d", n_groups,
-              kMaxGroups);
+  HGT_REQUIRE(n_groups >= 0, "hgt_typed_linear: n_groups=%d", n_groups);
   HGT_REQUIRE(K > 0 && cb_width > 0, "hgt_typed_linear: K=%d cb_width=%d", K, cb_width);
   if (n_groups == 0) return 0;
+  if (n_groups > kMaxGroups) {
+    // schemas with many <type, relation> pairs: the per-launch tile prefix holds kMaxGroups entries, so launch in
+    // chunks (same stream, same workspace: launches are ordered)
+    for (int g0 = 0; g0 < n_groups; g0 += kMaxGroups) {
+      const int n = n_groups - g0 < kMaxGroups ? n_groups - g0 : kMaxGroups;
+      int rc = hgt_typed_linear(A, lda, W, bias, K, cb_width, groups + g0, h_groups + g0, n, cblocks, out, impl,
+                                workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   if (impl == 0) impl = hgt_typed_linear_tc_supported(lda, K, cb_width) ? 2 : 1;
   if (impl == 2) {
     HGT_REQUIRE(hgt_typed_linear_tc_supported(lda, K, cb_width),

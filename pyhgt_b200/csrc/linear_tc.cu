@@ -874,6 +874,15 @@ extern "C" int hgt_typed_linear_presplit(const void* a_hi, const void* a_lo, con
   HGT_REQUIRE(K % 8 == 0 && hgt_typed_linear_tc_supported(K, K, cb_width),
               "hgt_typed_linear_presplit: unsupported shape K=%d cb_width=%d", K, cb_width);
   if (n_groups == 0) return 0;
+  if (n_groups > kMaxGroups) {                               // see hgt_typed_linear: chunked launches
+    for (int g0 = 0; g0 < n_groups; g0 += kMaxGroups) {
+      const int n = n_groups - g0 < kMaxGroups ? n_groups - g0 : kMaxGroups;
+      int rc = hgt_typed_linear_presplit(a_hi, a_lo, W, bias, K, cb_width, groups + g0, h_groups + g0, n, cblocks, out,
+                                         workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   return tc_run(nullptr, 0, reinterpret_cast<const __nv_bfloat16*>(a_hi), reinterpret_cast<const __nv_bfloat16*>(a_lo),
                 W, bias, K, cb_width, groups, h_groups, n_groups, cblocks, out, workspace, workspace_bytes,
                 (cudaStream_t)stream_);

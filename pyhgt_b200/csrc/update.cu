@@ -22,6 +22,7 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
   int t = 0;
   while (t < T && row >= type_row0[t + 1]) ++t;
   if (type_active && t < T && row - type_row0[t] >= type_active[t]) return;   // halo source: no output row
+  if (perm && perm[row] < 0) return;             // sharded out_map: -1 = row without an output (e.g. unknown-type halo)
   float* orow = out + (perm ? (int64_t)perm[row] : row) * d;
   if (t >= T) {                                  // type outside [0,T): the reference leaves zeros (conv.py:120)
     for (int c = lane; c < d; c += 32) orow[c] = 0.f;
@@ -111,6 +112,7 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
   int t = 0;
   while (t < T && row >= type_row0[t + 1]) ++t;
   if (type_active && t < T && row - type_row0[t] >= type_active[t]) return;
+  if (perm && perm[row] < 0) return;             // sharded out_map: -1 = row without an output
   float4* orow = reinterpret_cast<float4*>(out + (perm ? (int64_t)perm[row] : row) * d);
   if (t >= T) {
 #pragma unroll

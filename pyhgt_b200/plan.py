@@ -241,6 +241,10 @@ class LayerTables:
     type_active_dev: torch.Tensor = None
 
 
+class GroupTable(tuple):
+    """(groups_dev, groups_host, n_groups, cblocks_dev) plus `.c_host`, the host copy of the column-block table."""
+
+
 def _pack_groups(groups, cblocks, dev):
     g = np.zeros(max(len(groups), 1), dtype=_lib.LIN_GROUP_DTYPE)
     for i, t in enumerate(groups):
@@ -250,7 +254,9 @@ def _pack_groups(groups, cblocks, dev):
         c[i] = t
     g_dev = torch.from_numpy(g.view(np.uint8).copy()).to(dev)
     c_dev = torch.from_numpy(c.view(np.uint8).copy()).to(dev)
-    return (g_dev, g, len(groups), c_dev)
+    tab = GroupTable((g_dev, g, len(groups), c_dev))
+    tab.c_host = c                 # host copy of the column-block table (the backward pass sizes its launches with it)
+    return tab
 
 
 def layer_tables(plan, d_in, d_out, active=None):

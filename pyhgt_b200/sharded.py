@@ -169,25 +169,47 @@ class ShardedGraph:
             return out
         return src.index_select(0, idx32.long())
 
+    def _resolve_halo_mode(self, x_own):
+        """"auto" -> "p2p" or "nccl", decided ONCE and COLLECTIVELY: every rank tries the symmetric-memory rendezvous,
+        the success flags are all-reduced (MIN) and the ranks switch together — a rank-local fallback would leave some
+        ranks in NCCL's all_to_all and others in symmetric-memory barriers.  Only the rendezvous is guarded; kernel and
+        ABI errors of the pull path propagate."""
+        if self.halo_mode != "auto":
+            return
+        if not (x_own.is_cuda and self.world > 1):
+            self.halo_mode = "nccl"
+            return
+        ok, why = 1, ""
+        try:
+            self._symm_setup(x_own.shape[1], x_own.device)
+        except (RuntimeError, ImportError, AttributeError, NotImplementedError) as exc:   # symmetric memory unavailable
+            ok, why = 0, str(exc)
+        flag = torch.tensor([ok], dtype=torch.int32, device=x_own.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.halo_mode = "p2p"
+        else:
+            import warnings
+            if why:
+                warnings.warn("pyhgt_b200: symmetric-memory halo exchange unavailable on this rank (%s); all ranks use "
+                              "the NCCL all_to_all" % why)
+            self._symm = None
+            self.halo_mode = "nccl"
+
     def exchange(self, x_own, split=False):
         """[n_owned, d] owned rows -> [n_local, d] local rows in local (type-sorted) order.  With split=True returns
         (x_local, (hi, lo) or None): on the p2p path the rows also come back as the bf16 hi/lo operand split and the fp32
         copy is valid for the owned rows only."""
-        if self.halo_mode in ("p2p", "auto") and x_own.is_cuda and self.world > 1:
-            if self.halo_mode == "p2p":
-                return self._exchange_p2p(x_own, split)
-            try:
-                out = self._exchange_p2p(x_own, split)
-                self.halo_mode = "p2p"
-                return out
-            except Exception as exc:                                   # noqa: BLE001 — both paths are GPU paths
-                import warnings
-                warnings.warn("pyhgt_b200: symmetric-memory halo exchange unavailable (%s); using NCCL all_to_all" % exc)
-                self.halo_mode = "nccl"
-        elif self.halo_mode == "auto":
-            self.halo_mode = "nccl"
+        self._resolve_halo_mode(x_own)
+        if self.halo_mode == "p2p" and x_own.is_cuda and self.world > 1:
+            return self._exchange_p2p(x_own, split)
         res = self._exchange_nccl(x_own)
         return (res, None) if split else res
+
+    def halo_stats(self, d):
+        """Bytes this rank receives per layer (fp32 halo rows) and the rows involved."""
+        return {"halo_rows_rank": self.n_halo, "owned_rows_rank": self.n_owned,
+                "halo_bytes_rank": self.n_halo * d * 4, "mode": self.halo_mode}
 
     def _exchange_nccl(self, x_own):
         d = x_own.shape[1]
@@ -200,18 +222,21 @@ class ShardedGraph:
             dist.all_to_all_single(buf[self.n_owned:], send, self.recv_splits, self.send_splits, group=self.group)
         return self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
 
+    def _symm_setup(self, d, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        if self._symm is None or self._symm[0].shape[1] != d:
+            buf = symm_mem.empty((max(self.max_owned, 1), d), dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            self._symm = (buf, hdl)
+        return self._symm
+
     def _exchange_p2p(self, x_own, split=False):
         """Fused halo exchange: every rank publishes x_own in NVLink-mapped symmetric memory and ONE kernel pulls
         each local row (owned and halo alike) straight from its owner's HBM into type-sorted position — no send-side
         gather, no NCCL call, no re-ordering pass."""
-        import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         d = x_own.shape[1]
-        if self._symm is None or self._symm[0].shape[1] != d:
-            buf = symm_mem.empty((max(self.max_owned, 1), d), dtype=torch.float32, device=x_own.device)
-            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-            self._symm = (buf, hdl)
-        buf, hdl = self._symm
+        buf, hdl = self._symm_setup(d, x_own.device)
         hdl.barrier(channel=0)                       # peers finished reading the previous layer's rows
         buf[:self.n_owned].copy_(x_own)
         hdl.barrier(channel=1)                       # every rank's rows are published
@@ -243,23 +268,26 @@ class ShardedGraph:
                 if p.grad is not None:
                     dist.all_reduce(p.grad, group=self.group)
 
-    def forward(self, conv, x_own):
-        """One HGTConv layer on this rank's shard; returns the [n_owned, d] output rows (owned_global order)."""
+    def forward(self, conv, x_own, graph=None):
+        """One HGTConv layer on this rank's shard; returns the [n_owned, d] output rows (owned_global order).
+        `graph` = (node_type, edge_index, edge_type, edge_time) device tensors holding this rank's LOCAL graph, for
+        callers that stream the shard from the host every step (the plan is rebuilt when they change)."""
         from .conv import HGTConv
         with HGTConv._stage("halo_exchange"):
             x_local, x_split = self.exchange(x_own, split=x_own.is_cuda and conv.linear_impl in (0, 2))
+        l_nt, l_ei, l_et, l_tm = (self.node_type, self.edge_index, self.edge_type, self.edge_time) if graph is None else graph
         if x_local.is_cuda:
             # the update epilogue writes each owned row straight to its position in owned_global order
             if getattr(self, "_out_map", None) is None:
                 om = torch.full((self.n_owned + self.n_halo,), -1, dtype=torch.int32, device=x_local.device)
                 om[self.own_rows] = torch.arange(self.n_owned, dtype=torch.int32, device=x_local.device)
                 self._out_map = om
-            out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
-                                             self.edge_time if conv.use_RTE else None, want_att=False, save=False,
+            out, att, _ = conv._forward_impl(x_local, l_nt, l_ei, l_et,
+                                             l_tm if conv.use_RTE else None, want_att=False, save=False,
                                              active_per_type=self.active_per_type, out_map=self._out_map,
                                              out_rows=self.n_owned, x_split=x_split)
             return out
-        out, att, _ = conv._forward_impl(x_local, self.node_type, self.edge_index, self.edge_type,
-                                         self.edge_time if conv.use_RTE else None, want_att=False, save=False,
+        out, att, _ = conv._forward_impl(x_local, l_nt, l_ei, l_et,
+                                         l_tm if conv.use_RTE else None, want_att=False, save=False,
                                          active_per_type=self.active_per_type)
         return out.index_select(0, self.own_rows)

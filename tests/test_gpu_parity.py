@@ -495,3 +495,141 @@ def test_to_torch_device_ingest_prebuilds_plan():
                                              fx["edge_type"], None, num_types=len(fx["types"]),
                                              num_relations=len(edge_dict), n_heads=1, use_RTE=False)
     _close(out, ref, "layer on to_torch output")
+
+
+def _sampled_rows_vs_oracle(g, d, H, rte, n_with=1200, n_isolated=200, seed=5, variant=0, what=""):
+    """Full-size technique: the output rows of sampled destinations equal the CPU oracle run on their
+    1-hop induced subgraph, because a destination's row depends only on its in-edges and their sources."""
+    import pyhgt_b200
+    dev = _dev()
+    N = g.num_nodes
+    T, R = g.num_types, g.num_relations
+    torch.manual_seed(0)
+    m = pyhgt_b200.HGTConv(d, d, T, R, H, 0.2, True, rte).eval()
+    x = torch.randn(N, d, generator=torch.Generator().manual_seed(1))
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(dev)
+    m.edge_variant = variant
+    old_keep = pyhgt_b200.HGTConv.keep_att
+    try:
+        pyhgt_b200.HGTConv.keep_att = False
+        with torch.no_grad():
+            out = m(x.to(dev), g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev),
+                    g.edge_time.to(dev) if rte else None)
+    finally:
+        pyhgt_b200.HGTConv.keep_att = old_keep
+    assert torch.isfinite(out).all()
+    deg = torch.bincount(g.edge_index[1], minlength=N)
+    gen = torch.Generator().manual_seed(seed)
+    has_in = (deg > 0).nonzero(as_tuple=True)[0]
+    # always include the heaviest destinations (hub splitting / merge path)
+    hubs = torch.argsort(deg, descending=True)[:8]
+    sample = torch.unique(torch.cat([has_in[torch.randperm(has_in.numel(), generator=gen)[:n_with]], hubs,
+                                     (deg == 0).nonzero(as_tuple=True)[0][:n_isolated]]))
+    sel = torch.zeros(N, dtype=torch.bool); sel[sample] = True
+    e_sel = sel[g.edge_index[1]].nonzero(as_tuple=True)[0]
+    nodes = torch.unique(torch.cat([sample, g.edge_index[0, e_sel]]))
+    local = torch.full((N,), -1, dtype=torch.int64); local[nodes] = torch.arange(nodes.numel())
+    sub_ei = torch.stack([local[g.edge_index[0, e_sel]], local[g.edge_index[1, e_sel]]])
+    ref, _ = hgt_oracle.hgt_forward_ref_port(params, x[nodes], g.node_type[nodes], sub_ei, g.edge_type[e_sel],
+                                             g.edge_time[e_sel] if rte else None, num_types=T, num_relations=R,
+                                             n_heads=H, use_norm=True, use_RTE=rte)
+    _close(out[sample.to(dev)], ref[local[sample]], what + ": sampled destination rows vs oracle")
+    return int(deg.max())
+
+
+def test_full_size_c3_sampled_rows():
+    """BASELINE config 3 at FULL size: OAG-CS-shaped, 6 types / 10 relations incl. `self`, N=200 k, E=5 M, d=400
+    (d_k=50: the VEC=2 lane map), RTE on."""
+    g = synth.make_oag_shaped(1.0)
+    assert g.num_edges >= 4_900_000 and g.num_types == 6 and g.num_relations == 10
+    _sampled_rows_vs_oracle(g, 400, 8, True, n_with=600, n_isolated=0, what="full-size C3")
+
+
+def test_full_size_c5_16m_sampled_rows_including_hubs():
+    """BASELINE config 5 (16 M-edge member): power-law destinations, thousands of hub pieces merged by k_merge_partials;
+    the sample always contains the 8 heaviest destinations."""
+    g = synth.make_powerlaw(16_000_000)
+    max_deg = _sampled_rows_vs_oracle(g, 128, 8, False, n_with=800, n_isolated=100, what="C5-16M")
+    assert max_deg > 1024                                   # the hub path was exercised
+
+
+def test_typed_linear_more_groups_than_one_launch_holds():
+    """Schemas with > 64 <type, relation> groups: the entry point launches in chunks."""
+    import ctypes
+    from pyhgt_b200 import _lib, plan as P
+    dev = _dev()
+    K, width, n_g, m = 64, 32, 70, 37
+    gen = torch.Generator().manual_seed(0)
+    A = torch.randn(n_g * m, K, generator=gen)
+    W = torch.randn(n_g * width, K, generator=gen)
+    b = torch.randn(n_g * width, generator=gen)
+    groups = [(i * m, m, i * width, 1, i, 1) for i in range(n_g)]
+    cblocks = [(i * m * width, width) for i in range(n_g)]
+    for impl in (1, 2):
+        tab = P._pack_groups(groups, cblocks, dev)
+        out = torch.zeros(n_g * m * width, device=dev)
+        wsb = ctypes.c_size_t()
+        _lib.call("hgt_typed_linear_workspace_bytes", tab[1].ctypes.data, n_g, K, width, impl, ctypes.byref(wsb))
+        ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+        Ad, Wd, bd = A.to(dev), W.to(dev), b.to(dev)
+        _lib.call("hgt_typed_linear", Ad.data_ptr(), K, Wd.data_ptr(), bd.data_ptr(), K, width, tab[0].data_ptr(),
+                  tab[1].ctypes.data, n_g, tab[3].data_ptr(), out.data_ptr(), impl, ws.data_ptr(), ws.numel(),
+                  torch.cuda.current_stream().cuda_stream)
+        ref = torch.stack([A[i * m:(i + 1) * m].double() @ W[i * width:(i + 1) * width].double().t()
+                           + b[i * width:(i + 1) * width].double() for i in range(n_g)]).float()
+        _close(out.view(n_g, m, width), ref, "typed linear, 70 groups, impl %d" % impl, atol=1e-4)
+
+
+def test_backward_two_graphs_same_pairs_no_stale_tables():
+    """a sampled-subgraph loop builds a new plan per batch; the backward of the second graph must use
+    ITS column-block table even when the pair set is identical and the plan cache was cleared in between."""
+    import pyhgt_b200
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    torch.manual_seed(0)
+    m = pyhgt_b200.HGTConv(64, 64, 3, 2, 4, 0.0, True, False).to(dev).train()
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    old_keep = pyhgt_b200.HGTConv.keep_att
+    pyhgt_b200.HGTConv.keep_att = False
+    try:
+        for seed, n in ((1, 300), (2, 517)):                     # same <type, relation> pairs, different type counts
+            g = synth.make_random(n, 4 * n, 3, 2, seed=seed, sorted_types=True)
+            x = torch.randn(n, 64, generator=torch.Generator().manual_seed(seed))
+            xd = x.to(dev).requires_grad_(True)
+            P.clear_plan_cache()
+            out = m(xd, g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev))
+            w = torch.randn(n, 64, generator=torch.Generator().manual_seed(9))
+            (out * w.to(dev)).sum().backward()
+            xr = x.clone().requires_grad_(True)
+            for v in params.values():
+                v.grad = None
+            ref, _ = hgt_oracle.hgt_forward_ref_port(params, xr, g.node_type, g.edge_index, g.edge_type, None,
+                                                     num_types=3, num_relations=2, n_heads=4, use_norm=True,
+                                                     use_RTE=False)
+            (ref * w).sum().backward()
+            _close(out.detach(), ref.detach(), "graph %d out" % seed)
+            for got, exp, what in [(xd.grad, xr.grad, "d node_inp")] + \
+                    [(p.grad, params[k].grad, "d " + k) for k, p in m.named_parameters() if params[k].grad is not None]:
+                got = got.cpu()
+                scale = max(exp.abs().max().item(), 1e-6)
+                assert torch.allclose(got, exp, rtol=2e-3, atol=2e-3 * scale), \
+                    "graph %d %s: max abs err %.3g (scale %.3g)" % (seed, what, (got - exp).abs().max().item(), scale)
+            m.zero_grad()
+    finally:
+        pyhgt_b200.HGTConv.keep_att = old_keep
+
+
+def test_module_saves_after_inference_forward(tmp_path):
+    """torch.save(model) after an eval pass, then load and run again (OAG/train_paper_field.py:279,311)."""
+    import pyhgt_b200
+    dev = _dev()
+    fx = load_golden("c1_rte")
+    m = _module_from_fixture(fx, dev)
+    out = _run(m, fx, dev)
+    path = tmp_path / "model.pt"
+    torch.save(m, path)
+    m2 = torch.load(path, weights_only=False).to(dev).eval()
+    out2 = _run(m2, fx, dev)
+    assert torch.equal(out, out2)
+    _close(out2, fx["out"], "reloaded module")

@@ -81,3 +81,25 @@ def test_gnn_wrapper_state_dict_matches_reference_fixture():
             c["prev_norm"], c["last_norm"], c["use_RTE"])
     assert list(m.state_dict().keys()) == list(fx["state_dict"].keys())
     m.load_state_dict(fx["state_dict"], strict=True)
+
+
+def test_module_pickles_and_deep_copies_with_launch_caches():
+    """OAG/train_paper_field.py:279 `torch.save(model, ...)` right after an eval pass: the per-process launch caches
+    (ctypes argument blocks, pointer tables) must not travel with the module."""
+    import copy
+    import io
+    import pyhgt_b200
+    from pyhgt_b200 import _lib
+    m = pyhgt_b200.HGTConv(64, 64, 2, 1, 4)
+    m.__dict__["_args_cache"] = {("k",): (_lib.ConvArgs(), None, None, None)}     # what _forward_fused leaves behind
+    m._ptrs("wq", [l.weight for l in m.q_linears], torch.device("cpu"))
+    m2 = copy.deepcopy(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    for other in (m2, m3):
+        assert "_args_cache" not in other.__dict__ and other._ptr_tables == {}
+        for (k, a), (k2, b) in zip(m.state_dict().items(), other.state_dict().items()):
+            assert k == k2 and torch.equal(a, b)
+    assert "_args_cache" in m.__dict__                                            # the live module keeps its caches
