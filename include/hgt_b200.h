@@ -197,13 +197,61 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
 /* Backward of hgt_edge_forward (training; the reference differentiates the same ops with autograd,
  * OAG/train_paper_field.py:249).  Inputs: the forward's q / kv / kvr tables, its un-activated output
  * `agg` (apply_gelu = 0), the saved per-destination softmax statistics `stats` [N,2H] and the incoming
- * gradient `dagg` [N,d].  Outputs (all must be ZERO-initialised by the caller): dq [N,d],
- * dkv [rows+1,2d] (gradient of the [K'|V'] table; the last row belongs to the all-zero row and is to be
- * discarded), dkvr [P*240+1,2d] or NULL.  workspace: >= 256 bytes. */
+ * gradient `dagg` [N,d].  Outputs (ZERO-INITIALISED BY THIS CALL, on the stream): dq [N,d],
+ * dkv [kv_rows_total, 2d] (gradient of the [K'|V'] table; kv_rows_total counts the trailing all-zero row, whose
+ * gradient is to be discarded), dkvr [kvr_rows_total, 2d] or NULL.  workspace: >= 256 bytes. */
 int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const float* agg, const float* dagg,
                       const float* stats, const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
                       const int32_t* tiles, int32_t n_tiles, int64_t n_nodes, int32_t d, int32_t n_heads,
+                      int64_t kv_rows_total, int64_t kvr_rows_total,
                       float* dq, float* dkv, float* dkvr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the typed linears (training path).  For the group / column-block tables of the forward call:
+ *   dA[a_row0_g + m, k]             = sum_c sum_n dOut_c[m, n] * W[w_row0_g + c*cb_width + n, k]   (* gelu'(gelu_aux) if given)
+ *   dW[w_row0_g + c*cb_width + n,k] += sum_m dOut_c[m, n] * A[a_row0_g + m, k]
+ *   db[w_row0_g + c*cb_width + n]   += sum_m dOut_c[m, n]           (groups with has_bias)
+ * dout has the layout of the forward's `out` (flat buffer addressed through the column-block table, dout_elems
+ * elements).  dW / db are ACCUMULATED INTO (several groups may share W rows: the caller zero-initialises them once per
+ * step); dA is written (rows no group covers are zeroed) unless accumulate_dA != 0, in which case the product is added
+ * to its current content.  dA / dW / db may each be NULL to skip that product.
+ * Tensor-core path (impl 0 = auto, 2 = force): tcgen05 split-bf16 x3 like the forward; takes the operands either as
+ * fp32 (split here; the dout split pass also yields db) or already split by their producers (dout_hi/lo in dout's
+ * layout; a_hi/a_lo [rows, K] as left by hgt_act_split in the forward) — with a pre-split dout, db is NOT computed.
+ * impl 1 = fp32 SIMT kernels (any shape; also chosen automatically for cb_width % 8, K % 16, K < 64, overlapping groups
+ * such as the RTE tables, or tiny problems).  h_cblocks: HOST copy of the column-block table. */
+int hgt_typed_linear_bwd_workspace_bytes(const hgt_lin_group* h_groups, int32_t n_groups, const hgt_lin_cblock* h_cblocks,
+                                         int32_t K, int32_t cb_width, int64_t lda, int64_t dout_elems,
+                                         int32_t have_dout_split, int32_t have_a_split, int32_t impl, size_t* out_bytes);
+int hgt_typed_linear_bwd(const float* dout, const void* dout_hi, const void* dout_lo, int64_t dout_elems,
+                         const float* A, int64_t lda, const void* a_hi, const void* a_lo,
+                         const float* W, int32_t K, int32_t cb_width, const hgt_lin_group* groups,
+                         const hgt_lin_group* h_groups, int32_t n_groups, const hgt_lin_cblock* h_cblocks,
+                         float* dA, int32_t accumulate_dA, const float* gelu_aux, float* dW, float* db,
+                         int32_t impl, void* workspace, size_t workspace_bytes, void* stream);
+
+/* act(in) as fp32 (out_f32 [rows, K], or NULL) and/or as the bf16 hi/lo operand split (hi/lo [rows, K], or NULL; needs
+ * K % 8 == 0).  act: 0 = identity, 1 = exact-erf gelu (conv.py:119).  The training forward keeps the split for the
+ * backward pass (it is the A operand of the dW product). */
+int hgt_act_split(const float* in, int64_t ld, int64_t rows, int32_t K, int32_t act, float* out_f32,
+                  void* hi, void* lo, void* stream);
+
+/* Backward of hgt_update_epilogue (conv.py:129-133).  dout [N,d] in ORIGINAL node order (perm as in the forward);
+ * o / x [N,d] rank order (the forward's inputs); norm_w [T,d] or NULL.  Outputs: d_o, d_x [N,d] rank order (rows of
+ * out-of-range type get zeros), d_skip [T], d_norm_w / d_norm_b [T,d] (zero-initialised by this call). */
+int hgt_update_backward(const float* dout, const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
+                        const float* skip, const float* norm_w, const int32_t* perm, int64_t n_nodes, int32_t d,
+                        float* d_o, float* d_x, float* d_skip, float* d_norm_w, float* d_norm_b, void* stream);
+
+/* Backward of hgt_fold_weights for the K'/V' blocks: from d W_cat / d b_cat to the gradients of k_linears / v_linears
+ * (stacked [T, d_out, d_in] / [T, d_out]) and relation_att / relation_msg [R,H,dk,dk], relation_pri [R,H]; all outputs
+ * are zero-initialised by this call.  (The W_q rows of W_cat are plain copies: their gradient is the matching slice.) */
+int hgt_fold_backward(const float* d_w_cat, const float* d_b_cat, const float* const* wk, const float* const* bk,
+                      const float* const* wv, const float* const* bv, const float* relation_att,
+                      const float* relation_msg, const float* relation_pri, int32_t num_types, int32_t num_relations,
+                      int32_t n_heads, int32_t d_in, int32_t d_out, int32_t n_pairs, const int32_t* pair_type,
+                      const int32_t* pair_rel, const int32_t* cat_row0, float* d_wk, float* d_bk, float* d_wv,
+                      float* d_bv, float* d_att, float* d_msg, float* d_pri, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Update epilogue (conv.py:129-133): y = o*sigmoid(skip[t]) + x*(1-sigmoid(skip[t])); LayerNorm_t(y)

@@ -1,21 +1,24 @@
 """Training path of pyhgt_b200.HGTConv (reference: the same forward differentiated by autograd,
 OAG/train_paper_field.py:249 ``loss.backward()``).
 
-The graph-dependent, memory-bound part — score / softmax-by-destination / weighted aggregation — is ONE custom
-autograd.Function whose forward and backward are the hand-written kernels ``hgt_edge_forward`` /
-``hgt_edge_backward`` on the cached CSR plan (no per-edge intermediates are kept: backward recomputes the
-softmax weights from the saved per-destination (max, sum)).  The typed linears (Q / K' / V' projection, a_linears)
-run FORWARD through the same tcgen05 grouped GEMM as inference (``_TypedLinear``); their backward (dX, dW, db) uses
-cuBLAS fp32 GEMMs on strided views this round.  The relation-matrix fold and the gated-skip / LayerNorm are small
-differentiable torch ops, so gradients reach ``node_inp`` and every parameter of conv.py:28-54 including ``emb.*``.  The inference path
-(``torch.no_grad``) does not come through here: it uses the fused tcgen05 / epilogue kernels in conv.py.
+Every stage is a custom autograd.Function whose forward AND backward are hand-written kernels behind the C ABI:
+
+    _FoldWeights     hgt_fold_weights / hgt_fold_backward        relation_att/msg/pri folded into the typed K/V weights
+    _TypedLinear     hgt_act_split + hgt_typed_linear_presplit   typed projections, a_linears, RTE tables (tcgen05
+                     / hgt_typed_linear_bwd                      split-bf16 forward, dX and dW; fp32 SIMT for odd shapes);
+                                                                 the gelu in front of the a_linears (conv.py:119) lives in
+                                                                 the operand split (forward) and the dX epilogue (backward)
+    _EdgeAttention   hgt_edge_forward / hgt_edge_backward        score -> softmax by destination -> weighted aggregation
+    _UpdateEpilogue  hgt_update_epilogue / hgt_update_backward   sigmoid(skip) gate + LayerNorm (conv.py:129-133)
+
+No per-edge intermediates are kept: the edge backward recomputes the softmax weights from the saved per-destination
+(max, sum); the typed linears keep the bf16 hi/lo split of their input (the A operand of the dW product).  No cuBLAS,
+no torch matmul on this path.  Gradients reach ``node_inp`` and every parameter of conv.py:28-54 including ``emb.*``.
+The inference path (``torch.no_grad``) does not come through here: it uses the fused kernels in conv.py.
 """
 import ctypes
-import math
 
-import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from . import plan as _plan
@@ -25,163 +28,253 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-class _EdgeAttention(torch.autograd.Function):
-    """agg[i] = sum_{e -> i} softmax_i(<Q[i], K'[e]>) * V'[e]   (conv.py:99,108-111 + scatter-add)."""
+def _tc_shape_ok(K, width):
+    """Shapes both the tensor-core forward (hgt_typed_linear_presplit) and backward (hgt_typed_linear_bwd) take."""
+    return K % 16 == 0 and K >= 64 and width % 16 == 0
+
+
+class _TypedLinear(torch.autograd.Function):
+    """out_flat[cblock c of group g][m, :] = act(A)[rows_g] @ W_cat[rows of (g, c)]^T + b_cat   (act: 0 none, 1 gelu)."""
 
     @staticmethod
-    def forward(ctx, q, kv, kvr, plan, n_heads, want_att, variant):
-        N, d = q.shape
-        dev = q.device
+    def forward(ctx, a, w_cat, b_cat, table, width, out_elems, impl, act, zero_ranges):
+        g_dev, g_host, n_g, c_dev = table
+        a = a.contiguous()
+        w_cat = w_cat.contiguous()
+        rows, K = a.shape
+        dev = a.device
+        st = _stream()
+        out = torch.empty(out_elems, dtype=torch.float32, device=dev)
+        for (z0, z1) in zero_ranges:                                   # padding / all-zero table rows only
+            if z1 > z0:
+                out[z0:z1].zero_()
+        use_tc = impl in (0, 2) and _tc_shape_ok(K, width)
+        hi = lo = a_act = None
+        wsb = ctypes.c_size_t()
+        if use_tc:
+            hi = torch.empty((rows, K), dtype=torch.bfloat16, device=dev)
+            lo = torch.empty((rows, K), dtype=torch.bfloat16, device=dev)
+            _lib.call("hgt_act_split", a.data_ptr(), K, rows, K, act, None, hi.data_ptr(), lo.data_ptr(), st)
+            _lib.call("hgt_typed_linear_presplit_workspace_bytes", g_host.ctypes.data, n_g, K, width, ctypes.byref(wsb))
+            ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+            _lib.call("hgt_typed_linear_presplit", hi.data_ptr(), lo.data_ptr(), w_cat.data_ptr(), _lib.ptr(b_cat), K, width,
+                      g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                      ws.numel(), st)
+        else:
+            a_act = a
+            if act:
+                a_act = torch.empty_like(a)
+                _lib.call("hgt_act_split", a.data_ptr(), K, rows, K, act, a_act.data_ptr(), None, None, st)
+            _lib.call("hgt_typed_linear_workspace_bytes", g_host.ctypes.data, n_g, K, width, 1, ctypes.byref(wsb))
+            ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+            _lib.call("hgt_typed_linear", a_act.data_ptr(), K, w_cat.data_ptr(), _lib.ptr(b_cat), K, width,
+                      g_dev.data_ptr(), g_host.ctypes.data, n_g, c_dev.data_ptr(), out.data_ptr(), 1, ws.data_ptr(),
+                      ws.numel(), st)
+        ctx.table, ctx.width, ctx.has_bias, ctx.act, ctx.use_tc = table, width, b_cat is not None, act, use_tc
+        ctx.out_elems = out_elems
+        # gelu'(a) needs the un-activated input; the dW product needs act(a): as the bf16 split (tensor cores) or fp32
+        ctx.save_for_backward(a if (act or not use_tc) else None, a_act if (act and not use_tc) else None, hi, lo, w_cat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, a_act, hi, lo, w_cat = ctx.saved_tensors
+        g_dev, g_host, n_g, _ = ctx.table
+        c_host = ctx.table.c_host
+        width = ctx.width
+        K = w_cat.shape[1]
+        dev = w_cat.device
+        rows = hi.shape[0] if hi is not None else a.shape[0]
+        need_da = ctx.needs_input_grad[0]
+        dout = dout.contiguous()
+        da = torch.empty((rows, K), dtype=torch.float32, device=dev) if need_da else None
+        dw = torch.zeros_like(w_cat)                                   # small: [sum of out rows, K]
+        db = torch.zeros(w_cat.shape[0], dtype=torch.float32, device=dev) if ctx.has_bias else None
+        impl = 2 if ctx.use_tc else 1
+        a_f32 = a_act if a_act is not None else a                      # SIMT dW operand (act already applied)
+        wsb = ctypes.c_size_t()
+        _lib.call("hgt_typed_linear_bwd_workspace_bytes", g_host.ctypes.data, n_g, c_host.ctypes.data, K, width, K,
+                  ctx.out_elems, 0, int(hi is not None), impl, ctypes.byref(wsb))
+        ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+        _lib.call("hgt_typed_linear_bwd", dout.data_ptr(), None, None, ctx.out_elems, _lib.ptr(a_f32), K, _lib.ptr(hi),
+                  _lib.ptr(lo), w_cat.data_ptr(), K, width, g_dev.data_ptr(), g_host.ctypes.data, n_g,
+                  c_host.ctypes.data, _lib.ptr(da), 0, a.data_ptr() if ctx.act else None, dw.data_ptr(), _lib.ptr(db),
+                  impl, ws.data_ptr(), ws.numel(), _stream())
+        return da, dw, db, None, None, None, None, None, None
+
+
+class _EdgeAttention(torch.autograd.Function):
+    """agg[i] = sum_{e -> i} softmax_i(<Q[i], K'[e]>) * V'[e]   (conv.py:99,108-111 + scatter-add).  Takes and returns
+    the FLAT projection buffer (Q at q_off, the [K'|V'] table at kv_off): its gradient is produced as one buffer, so
+    autograd never assembles it from slices."""
+
+    @staticmethod
+    def forward(ctx, proj, kvr, plan, lt, d, n_heads, want_att, variant):
+        N = plan.n_nodes
+        dev = proj.device
+        proj = proj.contiguous()
+        q = proj[lt.q_off:lt.q_off + N * d]
+        kv = proj[lt.kv_off:]
         ws_bytes = ctypes.c_size_t()
         _lib.call("hgt_edge_workspace_bytes", plan.n_split, d, n_heads, ctypes.byref(ws_bytes))
         ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
         agg = torch.empty((N, d), dtype=torch.float32, device=dev)
         stats = torch.empty((N, 2 * n_heads), dtype=torch.float32, device=dev)
         att = torch.empty((plan.n_edges, n_heads), dtype=torch.float32, device=dev) if want_att else None
-        q, kv = q.contiguous(), kv.contiguous()
         kvr = None if kvr is None else kvr.contiguous()
         _lib.call("hgt_edge_forward", q.data_ptr(), kv.data_ptr(), _lib.ptr(kvr), plan.row_ptr.data_ptr(),
                   plan.kv_row.data_ptr(), None if kvr is None else plan.rte_row.data_ptr(), plan.csr_eid.data_ptr(),
-                  plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, plan.n_edges, d, n_heads, 0,
-                  agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), variant,
-                  _stream())
-        ctx.plan, ctx.n_heads, ctx.has_kvr = plan, n_heads, kvr is not None
-        ctx.save_for_backward(q, kv, kvr if kvr is not None else q.new_empty(0), agg, stats)
-        ctx.mark_non_differentiable(*([att] if att is not None else []))
-        return (agg, att) if att is not None else (agg, None)
+                  plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, plan.n_edges, d,
+                  n_heads, 0, agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                  variant, _stream())
+        ctx.plan, ctx.lt, ctx.d, ctx.n_heads, ctx.has_kvr = plan, lt, d, n_heads, kvr is not None
+        ctx.save_for_backward(proj, kvr, agg, stats)
+        if att is not None:
+            ctx.mark_non_differentiable(att)
+        return agg, att
 
     @staticmethod
     def backward(ctx, dagg, _datt=None):
-        q, kv, kvr, agg, stats = ctx.saved_tensors
-        plan, H = ctx.plan, ctx.n_heads
-        kvr = kvr if ctx.has_kvr else None
-        N, d = q.shape
-        dq = torch.zeros_like(q)
-        dkv = torch.zeros_like(kv)
-        dkvr = torch.zeros_like(kvr) if kvr is not None else None
-        ws = torch.empty(256, dtype=torch.uint8, device=q.device)
+        proj, kvr, agg, stats = ctx.saved_tensors
+        plan, lt, d, H = ctx.plan, ctx.lt, ctx.d, ctx.n_heads
+        N = plan.n_nodes
+        q = proj[lt.q_off:lt.q_off + N * d]
+        kv = proj[lt.kv_off:]
+        dproj = torch.empty_like(proj)                                 # hgt_edge_backward zero-initialises dq / dkv
+        if lt.kv_off > N * d:
+            dproj[N * d:lt.kv_off].zero_()                             # alignment gap
+        dq = dproj[lt.q_off:lt.q_off + N * d]
+        dkv = dproj[lt.kv_off:]
+        dkvr = torch.empty_like(kvr) if kvr is not None else None
+        ws = torch.empty(256, dtype=torch.uint8, device=proj.device)
         dagg = dagg.contiguous()
         _lib.call("hgt_edge_backward", q.data_ptr(), kv.data_ptr(), _lib.ptr(kvr), agg.data_ptr(), dagg.data_ptr(),
                   stats.data_ptr(), plan.row_ptr.data_ptr(), plan.kv_row.data_ptr(),
                   None if kvr is None else plan.rte_row.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, N, d, H,
+                  plan.kv_rows + 1, 0 if kvr is None else kvr.numel() // (2 * d),
                   dq.data_ptr(), dkv.data_ptr(), _lib.ptr(dkvr), ws.data_ptr(), ws.numel(), _stream())
-        return dq, dkv, dkvr, None, None, None, None
+        return dproj, dkvr, None, None, None, None, None, None
 
 
-class _TypedLinear(torch.autograd.Function):
-    """Grouped typed linear through the C ABI (``hgt_typed_linear``: tcgen05 split-bf16 when the shape allows).
-    forward : out_flat[cblock c of group g][m, :] = A[rows_g] @ W_cat[rows of (g, c)]^T + b_cat
-    backward: dA / dW_cat / db_cat with cuBLAS fp32 GEMMs on strided views of the flat gradient buffer (the
-              native split-bf16 dX / dW kernels are future work)."""
+class _FoldWeights(torch.autograd.Function):
+    """(W_cat, b_cat) of the typed projection: per type  [W_q ; K'_p ; V'_p ...]  (hgt_fold_weights, conv.py:96-104)."""
 
     @staticmethod
-    def forward(ctx, a, w_cat, b_cat, module, table, width, out_elems, impl):
-        g_dev, g_host, n_g, c_dev = table
-        a = a.contiguous()
-        w_cat = w_cat.contiguous()
-        out = torch.zeros(out_elems, dtype=torch.float32, device=a.device)
-        module._typed_linear(a, a.shape[1], w_cat, b_cat, a.shape[1], width, table, out, impl, _stream())
-        ctx.table, ctx.width, ctx.has_bias = table, width, b_cat is not None
-        ctx.cblocks_host = table.c_host                                # host copy kept with the table (plan._pack_groups)
-        ctx.save_for_backward(a, w_cat)
+    def forward(ctx, module, plan, lt, *params):
+        m = module
+        T, R, H, d_in, d = m.num_types, m.num_relations, m.n_heads, m.in_dim, m.out_dim
+        dev = params[0].device
+        st = _stream()
+        tabs = [m._ptrs(n, ts, dev) for n, ts in (("wq", [l.weight for l in m.q_linears]), ("bq", [l.bias for l in m.q_linears]),
+                                                 ("wk", [l.weight for l in m.k_linears]), ("bk", [l.bias for l in m.k_linears]),
+                                                 ("wv", [l.weight for l in m.v_linears]), ("bv", [l.bias for l in m.v_linears]))]
+        w_cat = torch.empty((max(lt.cat_rows, 1), d_in), dtype=torch.float32, device=dev)
+        b_cat = torch.empty(max(lt.cat_rows, 1), dtype=torch.float32, device=dev)
+        _lib.call("hgt_fold_weights", *[t.data_ptr() for t in tabs], m.relation_att.data_ptr(), m.relation_msg.data_ptr(),
+                  m.relation_pri.data_ptr(), T, R, H, d_in, d, plan.n_pairs, plan.pair_type_dev.data_ptr(),
+                  plan.pair_rel_dev.data_ptr(), lt.cat_row0_dev.data_ptr(), lt.q_row0_dev.data_ptr(), w_cat.data_ptr(),
+                  b_cat.data_ptr(), st)
+        ctx.module, ctx.plan, ctx.lt, ctx.tabs = m, plan, lt, tabs
+        return w_cat, b_cat
+
+    @staticmethod
+    def backward(ctx, dw_cat, db_cat):
+        m, plan, lt, tabs = ctx.module, ctx.plan, ctx.lt, ctx.tabs
+        T, R, H, d_in, d, dk = m.num_types, m.num_relations, m.n_heads, m.in_dim, m.out_dim, m.d_k
+        dev = dw_cat.device
+        dw_cat, db_cat = dw_cat.contiguous(), db_cat.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_wk, d_wv = torch.empty((T, d, d_in), **f32), torch.empty((T, d, d_in), **f32)
+        d_bk, d_bv = torch.empty((T, d), **f32), torch.empty((T, d), **f32)
+        d_att, d_msg = torch.empty((R, H, dk, dk), **f32), torch.empty((R, H, dk, dk), **f32)
+        d_pri = torch.empty((R, H), **f32)
+        _lib.call("hgt_fold_backward", dw_cat.data_ptr(), db_cat.data_ptr(), tabs[2].data_ptr(), tabs[3].data_ptr(),
+                  tabs[4].data_ptr(), tabs[5].data_ptr(), m.relation_att.data_ptr(), m.relation_msg.data_ptr(),
+                  m.relation_pri.data_ptr(), T, R, H, d_in, d, plan.n_pairs, plan.pair_type_dev.data_ptr(),
+                  plan.pair_rel_dev.data_ptr(), lt.cat_row0_dev.data_ptr(), d_wk.data_ptr(), d_bk.data_ptr(),
+                  d_wv.data_ptr(), d_bv.data_ptr(), d_att.data_ptr(), d_msg.data_ptr(), d_pri.data_ptr(), _stream())
+        # W_q / b_q rows of W_cat are plain copies: their gradient is the matching slice
+        d_wq = [dw_cat[lt.q_row0[t]:lt.q_row0[t] + d] for t in range(T)]
+        d_bq = [db_cat[lt.q_row0[t]:lt.q_row0[t] + d] for t in range(T)]
+        grads = d_wq + d_bq + list(d_wk.unbind(0)) + list(d_bk.unbind(0)) + list(d_wv.unbind(0)) + list(d_bv.unbind(0))
+        return (None, None, None) + tuple(grads) + (d_att, d_msg, d_pri)
+
+
+class _UpdateEpilogue(torch.autograd.Function):
+    """out[perm[k]] = LayerNorm_t(o[k] * sigmoid(skip[t]) + x[k] * (1 - sigmoid(skip[t])))   (conv.py:129-133)."""
+
+    @staticmethod
+    def forward(ctx, o, x, skip, norm_w, norm_b, plan, T):
+        N, d = o.shape
+        o, x = o.contiguous(), x.contiguous()
+        out = torch.empty((N, d), dtype=torch.float32, device=o.device)
+        perm = None if plan.sorted_types else plan.perm
+        _lib.call("hgt_update_epilogue", o.data_ptr(), x.data_ptr(), plan.type_row0_dev.data_ptr(), T, skip.data_ptr(),
+                  _lib.ptr(norm_w), _lib.ptr(norm_b), _lib.ptr(perm), None, N, d, out.data_ptr(), None, None, _stream())
+        ctx.plan, ctx.T, ctx.has_norm = plan, T, norm_w is not None
+        ctx.save_for_backward(o, x, skip, norm_w)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        a, w_cat = ctx.saved_tensors
-        _, g_host, n_g, _ = ctx.table
-        width, K = ctx.width, a.shape[1]
-        da = torch.zeros_like(a)
-        dw = torch.zeros_like(w_cat)
-        db = torch.zeros(w_cat.shape[0], dtype=torch.float32, device=a.device) if ctx.has_bias else None
+        o, x, skip, norm_w = ctx.saved_tensors
+        plan, T = ctx.plan, ctx.T
+        N, d = o.shape
+        dev = o.device
         dout = dout.contiguous()
-        for gi in range(n_g):
-            g = g_host[gi]
-            r0, m = int(g["a_row0"]), int(g["m"])
-            if m == 0:
-                continue
-            a_g = a[r0:r0 + m]
-            for c in range(int(g["n_cblocks"])):
-                cb = ctx.cblocks_host[int(g["cb_first"]) + c]
-                off, ld = int(cb["out_off"]), int(cb["ld"])
-                d_blk = torch.as_strided(dout, (m, width), (ld, 1), off)            # [m, width] view
-                w0 = int(g["w_row0"]) + c * width
-                da[r0:r0 + m].addmm_(d_blk, w_cat[w0:w0 + width])
-                dw[w0:w0 + width].addmm_(d_blk.t(), a_g)
-                if db is not None and int(g["has_bias"]):
-                    db[w0:w0 + width] += d_blk.sum(0)
-        return da, dw, db, None, None, None, None, None
+        d_o, d_x = torch.empty_like(o), torch.empty_like(x)
+        d_skip = torch.empty(T, dtype=torch.float32, device=dev)
+        d_nw = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
+        d_nb = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
+        perm = None if plan.sorted_types else plan.perm
+        _lib.call("hgt_update_backward", dout.data_ptr(), o.data_ptr(), x.data_ptr(), plan.type_row0_dev.data_ptr(), T,
+                  skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(perm), N, d, d_o.data_ptr(), d_x.data_ptr(),
+                  d_skip.data_ptr(), _lib.ptr(d_nw), _lib.ptr(d_nb), _stream())
+        return d_o, d_x, d_skip, d_nw, d_nb, None, None
 
 
-def _fold(w, b, rel, scale, H, dk):
-    """W'[h*dk+c, :] = scale[h] * sum_a rel[h,a,c] * W[h*dk+a, :]  (and the same for the bias): the per-head
-    right-multiplication of conv.py:98/104 moved into the weights."""
-    d_in = w.shape[1]
-    wf = torch.einsum("hac,hai->hci", rel, w.view(H, dk, d_in))
-    bf = torch.einsum("hac,ha->hc", rel, b.view(H, dk))
-    if scale is not None:
-        wf = wf * scale.view(H, 1, 1)
-        bf = bf * scale.view(H, 1)
-    return wf.reshape(H * dk, d_in), bf.reshape(H * dk)
+def typed_linear(a, w_cat, b_cat, table, width, out_elems, impl=0, act=0, zero_ranges=()):
+    return _TypedLinear.apply(a, w_cat, b_cat, table, width, out_elems, impl, act, tuple(zero_ranges))
 
 
 def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
-    dev = node_inp.device
-    d_in, d, H, T, R, dk = m.in_dim, m.out_dim, m.n_heads, m.num_types, m.num_relations, m.d_k
+    d_in, d, H, T, R = m.in_dim, m.out_dim, m.n_heads, m.num_types, m.num_relations
     plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if m.use_RTE else None, T, R)
     N, P = plan.n_nodes, plan.n_pairs
     if node_inp.shape[0] != N:
         raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
     x = node_inp if plan.sorted_types else node_inp.index_select(0, plan.perm.long())
-    rows = [slice(plan.type_row0[t], plan.type_row0[t + 1]) for t in range(T)]
-
-    # typed projections with the relation matrices folded in.  W_cat / b_cat are assembled with differentiable torch
-    # ops (tiny: the fold is O(P * d * d_in * d_k)); the big grouped GEMM runs through the C ABI (_TypedLinear).
     lt = _plan.layer_tables(plan, d_in, d)
-    pairs_of_type = [[] for _ in range(T)]
-    for p, (s_, _) in enumerate(plan.pairs):
-        pairs_of_type[s_].append(p)
-    folded = {}
-    for p, (s_, r) in enumerate(plan.pairs):
-        kw, kb = _fold(m.k_linears[s_].weight, m.k_linears[s_].bias, m.relation_att[r],
-                       m.relation_pri[r] / math.sqrt(dk), H, dk)
-        vw, vb = _fold(m.v_linears[s_].weight, m.v_linears[s_].bias, m.relation_msg[r], None, H, dk)
-        folded[p] = (torch.cat([kw, vw], 0), torch.cat([kb, vb], 0))            # [2d, d_in]: K' rows then V' rows
-    w_parts, b_parts = [], []
-    for t in range(T):                                                          # same row order as plan.layer_tables
-        w_parts.append(m.q_linears[t].weight)
-        b_parts.append(m.q_linears[t].bias)
-        for p in pairs_of_type[t]:
-            w_parts.append(folded[p][0])
-            b_parts.append(folded[p][1])
-    w_cat, b_cat = torch.cat(w_parts, 0), torch.cat(b_parts, 0)
-    proj = _TypedLinear.apply(x, w_cat, b_cat, m, lt.proj_groups, d, lt.proj_elems, m.linear_impl)
-    q = proj[lt.q_off:lt.q_off + N * d].view(N, d)
-    kv = proj[lt.kv_off:lt.kv_off + (plan.kv_rows + 1) * 2 * d].view(plan.kv_rows + 1, 2 * d)
+
+    # 1. relation matrices folded into the typed K/V weights; typed projections -> flat [Q | pad | K'V' table | zero row]
+    params = ([l.weight for l in m.q_linears] + [l.bias for l in m.q_linears] +
+              [l.weight for l in m.k_linears] + [l.bias for l in m.k_linears] +
+              [l.weight for l in m.v_linears] + [l.bias for l in m.v_linears] +
+              [m.relation_att, m.relation_msg, m.relation_pri])
+    w_cat, b_cat = _FoldWeights.apply(m, plan, lt, *params)
+    kv_end = lt.kv_off + plan.kv_rows * 2 * d
+    proj = typed_linear(x, w_cat, b_cat, lt.proj_groups, d, lt.proj_elems, m.linear_impl, 0,
+                        ((N * d, lt.kv_off), (kv_end, lt.proj_elems)))
     kvr = None
     if m.use_RTE:
-        rt = F.linear(m.emb.emb.weight, m.emb.lin.weight, m.emb.lin.bias)        # [240, d_in], conv.py:299
-        kvr = torch.cat([F.linear(rt, folded[p][0]) for p in range(P)] + [x.new_zeros(1, 2 * d)], 0)
+        # RT = lin(emb.weight) [240, d_in] (conv.py:299), then projected with every pair's K'/V' weights (no bias)
+        rt = typed_linear(m.emb.emb.weight, m.emb.lin.weight, m.emb.lin.bias, lt.rt_group, d_in,
+                          _plan.RTE_MAX_LEN * d_in, 1).view(_plan.RTE_MAX_LEN, d_in)
+        n_kvr = (P * _plan.RTE_MAX_LEN + 1) * 2 * d
+        kvr = typed_linear(rt, w_cat, None, lt.rte_groups, d, n_kvr, 1, 0, ((P * _plan.RTE_MAX_LEN * 2 * d, n_kvr),))
 
-    tail = N - plan.type_row0[T]                                                 # nodes of unknown type (conv.py:120)
-    agg, att = _EdgeAttention.apply(q, kv, kvr, plan, H, bool(m.keep_att), m.edge_variant)
+    # 2. fused edge kernel
+    agg, att = _EdgeAttention.apply(proj, kvr, plan, lt, d, H, bool(m.keep_att), m.edge_variant)
     m.att = att
 
-    g = F.gelu(agg)                                                              # conv.py:119
+    # 3. a_linears on gelu(agg) (conv.py:119,125): the gelu is applied inside the operand split / the dX epilogue
     wa_cat = torch.cat([l.weight for l in m.a_linears], 0)
     ba_cat = torch.cat([l.bias for l in m.a_linears], 0)
-    o_all = _TypedLinear.apply(g, wa_cat, ba_cat, m, lt.upd_groups, d, N * d, m.linear_impl).view(N, d)
-    outs = []
-    for t in range(T):
-        o = m.drop(o_all[rows[t]])                                               # conv.py:125
-        alpha = torch.sigmoid(m.skip[t])                                         # conv.py:129
-        y = o * alpha + x[rows[t]] * (1 - alpha)
-        if m.use_norm:
-            y = m.norms[t](y)
-        outs.append(y)
-    if tail:
-        outs.append(x.new_zeros(tail, d))                                        # conv.py:120: rows stay zero
-    out = torch.cat(outs, 0)
-    if not plan.sorted_types:
-        out = out.index_select(0, plan.rank.long())
-    return out
+    o = typed_linear(agg, wa_cat, ba_cat, lt.upd_groups, d, N * d, m.linear_impl, 1).view(N, d)
+    if m.training and m.drop.p > 0:
+        o = m.drop(o)                                                            # conv.py:125
+
+    # 4. gated skip + LayerNorm, written in original node order; rows of unknown type stay zero (conv.py:120)
+    norm_w = torch.stack([n.weight for n in m.norms]) if m.use_norm else None
+    norm_b = torch.stack([n.bias for n in m.norms]) if m.use_norm else None
+    return _UpdateEpilogue.apply(o, x, m.skip, norm_w, norm_b, plan, T)

@@ -28,7 +28,7 @@ struct BwdParams {
   const int32_t* tiles;
   int32_t n_tiles;
   int32_t d, H, DK, LPH, lph_shift;
-  float* dq;                 // [N, d]   zero-initialised by the caller
+  float* dq;                 // [N, d]   zero-initialised by hgt_edge_backward
   float* dkv;                // [rows+1, 2d] zero-initialised
   float* dkvr;               // [P*240+1, 2d] zero-initialised or nullptr
   int32_t* tile_counter;
@@ -199,13 +199,19 @@ int dispatch(const BwdParams& p, int nch, int grid, cudaStream_t st) {
 extern "C" int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const float* agg,
                                  const float* dagg, const float* stats, const int32_t* row_ptr,
                                  const int32_t* kv_row, const int32_t* rte_row, const int32_t* tiles, int32_t n_tiles,
-                                 int64_t n_nodes, int32_t d, int32_t n_heads, float* dq, float* dkv, float* dkvr,
+                                 int64_t n_nodes, int32_t d, int32_t n_heads, int64_t kv_rows_total,
+                                 int64_t kvr_rows_total, float* dq, float* dkv, float* dkvr,
                                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(n_heads >= 1 && n_heads <= 32 && d % n_heads == 0, "hgt_edge_backward: bad d=%d / n_heads=%d", d, n_heads);
   HGT_REQUIRE((kvr != nullptr) == (rte_row != nullptr) && (kvr != nullptr) == (dkvr != nullptr),
               "hgt_edge_backward: kvr, rte_row and dkvr must go together");
   HGT_REQUIRE(workspace && workspace_bytes >= 256, "hgt_edge_backward: workspace too small");
+  // the kernel accumulates (dk / dv of a <source, relation> row come from many edges): this call owns the initialisation
+  if (n_nodes > 0) HGT_CHECK_CUDA(cudaMemsetAsync(dq, 0, (size_t)n_nodes * d * sizeof(float), st));
+  if (kv_rows_total > 0) HGT_CHECK_CUDA(cudaMemsetAsync(dkv, 0, (size_t)kv_rows_total * 2 * d * sizeof(float), st));
+  if (dkvr && kvr_rows_total > 0)
+    HGT_CHECK_CUDA(cudaMemsetAsync(dkvr, 0, (size_t)kvr_rows_total * 2 * d * sizeof(float), st));
   if (n_nodes == 0 || n_tiles == 0) return 0;
   BwdParams p;
   p.q = q; p.kv = kv; p.kvr = kvr; p.agg = agg; p.dagg = dagg; p.stats = stats; p.row_ptr = row_ptr;
