@@ -238,7 +238,8 @@ int hgt_act_split(const float* in, int64_t ld, int64_t rows, int32_t K, int32_t 
 
 /* Backward of hgt_update_epilogue (conv.py:129-133).  dout [N,d] in ORIGINAL node order (perm as in the forward);
  * o / x [N,d] rank order (the forward's inputs); norm_w [T,d] or NULL.  Outputs: d_o, d_x [N,d] rank order (rows of
- * out-of-range type get zeros), d_skip [T], d_norm_w / d_norm_b [T,d] (zero-initialised by this call). */
+ * out-of-range type get zeros), d_skip [T], d_norm_w / d_norm_b [T,d] (zero-initialised by this call).
+ * skip == NULL: residual mode (y = o + x), d_skip is not touched. */
 int hgt_update_backward(const float* dout, const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
                         const float* skip, const float* norm_w, const int32_t* perm, int64_t n_nodes, int32_t d,
                         float* d_o, float* d_x, float* d_skip, float* d_norm_w, float* d_norm_b, void* stream);
@@ -256,6 +257,7 @@ int hgt_fold_backward(const float* d_w_cat, const float* d_b_cat, const float* c
 /* ------------------------------------------------------------------------------------------------
  * Update epilogue (conv.py:129-133): y = o*sigmoid(skip[t]) + x*(1-sigmoid(skip[t])); LayerNorm_t(y)
  * (eps 1e-5, affine) iff use_norm; rows of out-of-range type are written as zeros (conv.py:120).
+ * skip == NULL selects the plain residual y = o + x of DenseHGTConv (conv.py:261,273).
  *   o [N,d] rank order (a_linear output, after dropout if training);  x [N,d] rank order;
  *   type_row0 [T+2] int32 prefix of type_count;  norm_w/norm_b [T,d] or NULL;  perm NULL if identity;
  *   type_active [T] int32 or NULL: when given, only the first type_active[t] rows of type t are written

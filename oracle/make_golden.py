@@ -81,6 +81,13 @@ def dense_case(name, graph, d, heads, use_norm, use_RTE, seed):
           "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
           "node_inp": x, "node_type": graph.node_type, "edge_index": graph.edge_index,
           "edge_type": graph.edge_type, "edge_time": graph.edge_time, "out": out, "att": m.att.detach().clone()}
+    # gradients of sum(out * w) from the reference's own autograd (training path of the dense variant)
+    xg = x.clone().requires_grad_(True)
+    w = torch.randn(graph.num_nodes, d, generator=g)
+    (m(xg, graph.node_type, graph.edge_index, graph.edge_type, graph.edge_time) * w).sum().backward()
+    fx["grad_weight"] = w
+    fx["grad_node_inp"] = xg.grad.detach().clone()
+    fx["grad_params"] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
     path = os.path.join(OUT_DIR, name + ".pt")
     torch.save(fx, path)
     print("%-28s N=%d E=%d d=%d H=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, d, heads,
@@ -104,6 +111,12 @@ def gnn_case(name, graph, in_dim, n_hid, heads, n_layers, seed):
           "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
           "node_feature": x, "node_type": graph.node_type, "edge_index": graph.edge_index,
           "edge_type": graph.edge_type, "edge_time": graph.edge_time, "out": out.clone()}
+    xg = x.clone().requires_grad_(True)
+    w = torch.randn(graph.num_nodes, n_hid, generator=g)
+    (m(xg, graph.node_type, graph.edge_time, graph.edge_index, graph.edge_type) * w).sum().backward()
+    fx["grad_weight"] = w
+    fx["grad_node_feature"] = xg.grad.detach().clone()
+    fx["grad_params"] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
     path = os.path.join(OUT_DIR, name + ".pt")
     torch.save(fx, path)
     print("%-28s N=%d E=%d  %.0f KB" % (name, graph.num_nodes, graph.num_edges, os.path.getsize(path) / 1024))

@@ -201,36 +201,36 @@ class _FoldWeights(torch.autograd.Function):
 
 
 class _UpdateEpilogue(torch.autograd.Function):
-    """out[perm[k]] = LayerNorm_t(o[k] * sigmoid(skip[t]) + x[k] * (1 - sigmoid(skip[t])))   (conv.py:129-133)."""
+    """out[perm[k]] = LayerNorm_t(o[k] * sigmoid(skip[t]) + x[k] * (1 - sigmoid(skip[t])))   (conv.py:129-133);
+    skip=None: the plain residual o + x of DenseHGTConv (conv.py:261,273).  type_row0: [T+2] int32 row prefix (rows past
+    type_row0[T] are written as zeros), perm: rank-order row -> output row, or None."""
 
     @staticmethod
-    def forward(ctx, o, x, skip, norm_w, norm_b, plan, T):
+    def forward(ctx, o, x, skip, norm_w, norm_b, type_row0, T, perm):
         N, d = o.shape
         o, x = o.contiguous(), x.contiguous()
         out = torch.empty((N, d), dtype=torch.float32, device=o.device)
-        perm = None if plan.sorted_types else plan.perm
-        _lib.call("hgt_update_epilogue", o.data_ptr(), x.data_ptr(), plan.type_row0_dev.data_ptr(), T, skip.data_ptr(),
+        _lib.call("hgt_update_epilogue", o.data_ptr(), x.data_ptr(), type_row0.data_ptr(), T, _lib.ptr(skip),
                   _lib.ptr(norm_w), _lib.ptr(norm_b), _lib.ptr(perm), None, N, d, out.data_ptr(), None, None, _stream())
-        ctx.plan, ctx.T, ctx.has_norm = plan, T, norm_w is not None
-        ctx.save_for_backward(o, x, skip, norm_w)
+        ctx.T, ctx.has_norm, ctx.has_skip = T, norm_w is not None, skip is not None
+        ctx.save_for_backward(o, x, skip, norm_w, type_row0, perm)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        o, x, skip, norm_w = ctx.saved_tensors
-        plan, T = ctx.plan, ctx.T
+        o, x, skip, norm_w, type_row0, perm = ctx.saved_tensors
+        T = ctx.T
         N, d = o.shape
         dev = o.device
         dout = dout.contiguous()
         d_o, d_x = torch.empty_like(o), torch.empty_like(x)
-        d_skip = torch.empty(T, dtype=torch.float32, device=dev)
+        d_skip = torch.empty(T, dtype=torch.float32, device=dev) if ctx.has_skip else None
         d_nw = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
         d_nb = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
-        perm = None if plan.sorted_types else plan.perm
-        _lib.call("hgt_update_backward", dout.data_ptr(), o.data_ptr(), x.data_ptr(), plan.type_row0_dev.data_ptr(), T,
-                  skip.data_ptr(), _lib.ptr(norm_w), _lib.ptr(perm), N, d, d_o.data_ptr(), d_x.data_ptr(),
-                  d_skip.data_ptr(), _lib.ptr(d_nw), _lib.ptr(d_nb), _stream())
-        return d_o, d_x, d_skip, d_nw, d_nb, None, None
+        _lib.call("hgt_update_backward", dout.data_ptr(), o.data_ptr(), x.data_ptr(), type_row0.data_ptr(), T,
+                  _lib.ptr(skip), _lib.ptr(norm_w), _lib.ptr(perm), N, d, d_o.data_ptr(), d_x.data_ptr(),
+                  _lib.ptr(d_skip), _lib.ptr(d_nw), _lib.ptr(d_nb), _stream())
+        return d_o, d_x, d_skip, d_nw, d_nb, None, None, None
 
 
 def typed_linear(a, w_cat, b_cat, table, width, out_elems, impl=0, act=0, zero_ranges=()):
@@ -277,4 +277,65 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
     # 4. gated skip + LayerNorm, written in original node order; rows of unknown type stay zero (conv.py:120)
     norm_w = torch.stack([n.weight for n in m.norms]) if m.use_norm else None
     norm_b = torch.stack([n.bias for n in m.norms]) if m.use_norm else None
-    return _UpdateEpilogue.apply(o, x, m.skip, norm_w, norm_b, plan, T)
+    return _UpdateEpilogue.apply(o, x, m.skip, norm_w, norm_b, plan.type_row0_dev, T,
+                                 None if plan.sorted_types else plan.perm)
+
+
+def dense_hgt_forward(m, node_inp, node_type, edge_index, edge_type, edge_time):
+    """DenseHGTConv.forward (conv.py:143-280): the same message() => the same projection / edge kernels, then
+        y   = LayerNorm_t(drop(a_linear_t(agg)) + x)                     conv.py:261-266   (no gelu, no skip gate)
+        out = out_norm(drop(out_linear(gelu(mid_linear(y)))) + y)        conv.py:273-274   (FFN shared by all types)
+    built from the same differentiable stages: typed GEMMs (the gelu of the FFN sits in the operand split of out_linear
+    and in the dX epilogue of its backward) and the residual mode of the update epilogue.  Used for inference and
+    training alike (under no_grad the stages simply do not record)."""
+    d_in, d, H, T, R = m.in_dim, m.out_dim, m.n_heads, m.num_types, m.num_relations
+    plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if m.use_RTE else None, T, R)
+    N, P = plan.n_nodes, plan.n_pairs
+    if node_inp.shape[0] != N:
+        raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
+    dev = node_inp.device
+    x = node_inp if plan.sorted_types else node_inp.index_select(0, plan.perm.long())
+    lt = _plan.layer_tables(plan, d_in, d)
+    params = ([l.weight for l in m.q_linears] + [l.bias for l in m.q_linears] +
+              [l.weight for l in m.k_linears] + [l.bias for l in m.k_linears] +
+              [l.weight for l in m.v_linears] + [l.bias for l in m.v_linears] +
+              [m.relation_att, m.relation_msg, m.relation_pri])
+    w_cat, b_cat = _FoldWeights.apply(m, plan, lt, *params)
+    kv_end = lt.kv_off + plan.kv_rows * 2 * d
+    proj = typed_linear(x, w_cat, b_cat, lt.proj_groups, d, lt.proj_elems, m.linear_impl, 0,
+                        ((N * d, lt.kv_off), (kv_end, lt.proj_elems)))
+    kvr = None
+    if m.use_RTE:
+        rt = typed_linear(m.emb.emb.weight, m.emb.lin.weight, m.emb.lin.bias, lt.rt_group, d_in,
+                          _plan.RTE_MAX_LEN * d_in, 1).view(_plan.RTE_MAX_LEN, d_in)
+        n_kvr = (P * _plan.RTE_MAX_LEN + 1) * 2 * d
+        kvr = typed_linear(rt, w_cat, None, lt.rte_groups, d, n_kvr, 1, 0, ((P * _plan.RTE_MAX_LEN * 2 * d, n_kvr),))
+    agg, att = _EdgeAttention.apply(proj, kvr, plan, lt, d, H, bool(m.keep_att), m.edge_variant)
+    m.att = att
+
+    drop = m.training and m.drop.p > 0
+    wa_cat = torch.cat([l.weight for l in m.a_linears], 0)
+    ba_cat = torch.cat([l.bias for l in m.a_linears], 0)
+    o = typed_linear(agg, wa_cat, ba_cat, lt.upd_groups, d, N * d, m.linear_impl, 0).view(N, d)     # conv.py:261
+    if drop:
+        o = m.drop(o)
+    norm_w = torch.stack([n.weight for n in m.norms]) if m.use_norm else None
+    norm_b = torch.stack([n.bias for n in m.norms]) if m.use_norm else None
+    y = _UpdateEpilogue.apply(o, x, None, norm_w, norm_b, plan.type_row0_dev, T, None)              # rank order
+
+    n_known = plan.type_row0[T]
+    key = ("dense_ffn", d)
+    tabs = plan._layer_tables.get(key)
+    if tabs is None:
+        one = lambda w_: _plan._pack_groups([(0, n_known, 0, 1, 0, 1)], [(0, w_)], dev)            # noqa: E731
+        tabs = plan._layer_tables[key] = (one(2 * d), one(d),
+                                          torch.tensor([0, n_known, N], dtype=torch.int32).to(dev))
+    hmid = typed_linear(y, m.mid_linear.weight, m.mid_linear.bias, tabs[0], 2 * d, N * 2 * d, m.linear_impl, 0,
+                        ((n_known * 2 * d, N * 2 * d),)).view(N, 2 * d)
+    z = typed_linear(hmid, m.out_linear.weight, m.out_linear.bias, tabs[1], d, N * d, m.linear_impl, 1,
+                     ((n_known * d, N * d),)).view(N, d)                                             # gelu inside
+    if drop:
+        z = m.drop(z)
+    # shared out_norm over every known row, residual with y, written in original node order; unknown types -> zeros
+    return _UpdateEpilogue.apply(z, y, None, m.out_norm.weight.view(1, d), m.out_norm.bias.view(1, d), tabs[2], 1,
+                                 None if plan.sorted_types else plan.perm)

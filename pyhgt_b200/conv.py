@@ -442,9 +442,9 @@ class DenseHGTConv(HGTConv):
     softmax by destination, aggregation => the same CUDA kernels), but update() is
         y = LayerNorm_t(a_linear_t(agg) + x)                         (no gelu, no skip gate; conv.py:261-266)
         out = out_norm(out_linear(gelu(mid_linear(y))) + y)          (shared 2-layer FFN; conv.py:273-274)
-    The message/aggregate part and the three linears run through the C ABI (edge kernel, tcgen05 typed GEMM);
-    the residual / LayerNorm / gelu glue of this variant is torch elementwise code.
-    Parameter names match the reference (mid_linear, out_linear, out_norm; no `skip`).  Inference path only."""
+    Every stage runs through the C ABI (autograd.dense_hgt_forward): typed tcgen05 GEMMs with the FFN's gelu inside the
+    operand split, the residual + LayerNorm in `hgt_update_epilogue`'s residual mode; training uses the same native backward
+    kernels as HGTConv.  Parameter names match the reference (mid_linear, out_linear, out_norm; no `skip`)."""
     _has_skip = False
 
     def __init__(self, in_dim, out_dim, num_types, num_relations, n_heads, dropout=0.2, use_norm=True,
@@ -456,37 +456,8 @@ class DenseHGTConv(HGTConv):
 
     def forward(self, node_inp, node_type, edge_index, edge_type, edge_time=None):
         self._check_inputs(node_inp, edge_time)
-        if torch.is_grad_enabled() and (node_inp.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("pyhgt_b200.DenseHGTConv: inference only (call under torch.no_grad())")
-        c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att=self.keep_att, save=False,
-                       active_per_type=None, gelu_before_a=False)
-        self.att = c["att"]
-        plan, o, x, N, d, T, st = c["plan"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
-        y = o + x                                                         # conv.py:261
-        if self.use_norm:
-            for t in range(T):
-                r = slice(plan.type_row0[t], plan.type_row0[t + 1])
-                if r.stop > r.start:
-                    y[r] = F.layer_norm(y[r], (d,), self.norms[t].weight, self.norms[t].bias, 1e-5)
-        n_known = plan.type_row0[T]
-        one = lambda m_, k_, w_: _plan._pack_groups([(0, m_, 0, 1, 0, 1)], [(0, w_)], y.device)
-        key = ("dense_ffn", d, n_known)
-        tabs = plan._layer_tables.get(key)
-        if tabs is None:
-            tabs = plan._layer_tables[key] = (one(n_known, d, 2 * d), one(n_known, 2 * d, d))
-        hmid = torch.empty((N, 2 * d), dtype=torch.float32, device=y.device)
-        self._typed_linear(y, d, self.mid_linear.weight, self.mid_linear.bias, d, 2 * d, tabs[0], hmid,
-                           self.linear_impl, st)
-        hmid = F.gelu(hmid)
-        z = torch.empty((N, d), dtype=torch.float32, device=y.device)
-        self._typed_linear(hmid, 2 * d, self.out_linear.weight, self.out_linear.bias, 2 * d, d, tabs[1], z,
-                           self.linear_impl, st)
-        res = F.layer_norm(z + y, (d,), self.out_norm.weight, self.out_norm.bias, 1e-5)   # conv.py:273-274
-        if n_known < N:
-            res[n_known:] = 0                                             # unknown-type rows stay zero (conv.py:256)
-        if not plan.sorted_types:
-            res = res.index_select(0, plan.rank.long())
-        return res
+        from .autograd import dense_hgt_forward
+        return dense_hgt_forward(self, node_inp, node_type, edge_index, edge_type, edge_time)
 
 
 class GeneralConv(nn.Module):

@@ -28,7 +28,9 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
     for (int c = lane; c < d; c += 32) orow[c] = 0.f;
     return;
   }
-  const float alpha = 1.0f / (1.0f + __expf(-skip[t]));    // torch.sigmoid(self.skip[t]), conv.py:129
+  // skip == NULL: plain residual y = o + x (DenseHGTConv, conv.py:261,273)
+  const float alpha = skip ? 1.0f / (1.0f + __expf(-skip[t])) : 1.0f;    // torch.sigmoid(self.skip[t]), conv.py:129
+  const float beta = skip ? 1.0f - alpha : 1.0f;
   const float* op = o + row * d;
   const float* xp = x + row * d;
   float y[kMaxPerLane];
@@ -37,7 +39,7 @@ k_update_epilogue(const float* __restrict__ o, const float* __restrict__ x, cons
   for (int i = 0; i < kMaxPerLane; ++i) {
     int c = lane + i * 32;
     if (c < d) {
-      y[i] = op[c] * alpha + xp[c] * (1.0f - alpha);       // conv.py:131,133
+      y[i] = op[c] * alpha + xp[c] * beta;                 // conv.py:131,133
       sum += y[i];
     } else {
       y[i] = 0.f;
@@ -125,8 +127,8 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
     }
     return;
   }
-  const float alpha = 1.0f / (1.0f + __expf(-skip[t]));
-  const float beta = 1.0f - alpha;
+  const float alpha = skip ? 1.0f / (1.0f + __expf(-skip[t])) : 1.0f;
+  const float beta = skip ? 1.0f - alpha : 1.0f;
   float4 y[NV];
   float sum = 0.f;
 #pragma unroll

@@ -42,12 +42,15 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
   int cur_t = -1;
   auto flush = [&](int t) {
     if (t < 0 || t >= T) return;
-    const float a = 1.0f / (1.0f + __expf(-skip[t]));
-    float da = acc_a;
-    for (int s = 16; s > 0; s >>= 1) da += __shfl_xor_sync(0xffffffffu, da, s);
-    da *= a * (1.0f - a);
+    float da = 0.f;
+    if (skip) {
+      const float a = 1.0f / (1.0f + __expf(-skip[t]));
+      da = acc_a;
+      for (int s = 16; s > 0; s >>= 1) da += __shfl_xor_sync(0xffffffffu, da, s);
+      da *= a * (1.0f - a);
+    }
     if (uniform) {
-      if (lane == 0) atomicAdd(&s_red[2 * d], da);
+      if (lane == 0 && skip) atomicAdd(&s_red[2 * d], da);
       if (norm_w) {
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
@@ -56,7 +59,7 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
         }
       }
     } else {
-      if (lane == 0) atomicAdd(d_skip + t, da);
+      if (lane == 0 && skip) atomicAdd(d_skip + t, da);
       if (norm_w) {
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
@@ -86,7 +89,8 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
       }
       continue;
     }
-    const float a = 1.0f / (1.0f + __expf(-skip[t]));
+    const float a = skip ? 1.0f / (1.0f + __expf(-skip[t])) : 1.0f;
+    const float b1 = skip ? 1.0f - a : 1.0f;
     const float* gr = dout + (perm ? (int64_t)perm[row] : row) * d;
     const float* orow = o + row * d;
     const float* xrow = x + row * d;
@@ -99,7 +103,7 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
         const float ov = orow[c], xv = xrow[c];
         g[i] = gr[c];
         df[i] = ov - xv;
-        y[i] = ov * a + xv * (1.0f - a);
+        y[i] = ov * a + xv * b1;
         sum += y[i];
       } else {
         g[i] = df[i] = y[i] = 0.f;
@@ -146,7 +150,7 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
       const int c = lane + 32 * i;
       if (c < d) {
         dorow[c] = a * g[i];
-        dxrow[c] = (1.0f - a) * g[i];
+        dxrow[c] = b1 * g[i];
         acc_a = fmaf(g[i], df[i], acc_a);
       }
     }
@@ -161,7 +165,7 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
           atomicAdd(d_nb + (int64_t)t_first * d + i, s_red[d + i]);
         }
       }
-      if (threadIdx.x == 0) atomicAdd(d_skip + t_first, s_red[2 * d]);
+      if (threadIdx.x == 0 && skip) atomicAdd(d_skip + t_first, s_red[2 * d]);
     }
   }
 }
@@ -260,10 +264,10 @@ extern "C" int hgt_update_backward(const float* dout, const float* o, const floa
                                    int64_t n_nodes, int32_t d, float* d_o, float* d_x, float* d_skip, float* d_norm_w,
                                    float* d_norm_b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  HGT_REQUIRE(dout && o && x && type_row0 && skip && d_o && d_x && d_skip, "hgt_update_backward: NULL argument");
+  HGT_REQUIRE(dout && o && x && type_row0 && d_o && d_x && (d_skip || !skip), "hgt_update_backward: NULL argument");
   HGT_REQUIRE(d >= 1 && d <= 1024, "hgt_update_backward: d=%d unsupported (max 1024)", d);
   HGT_REQUIRE(!norm_w || (d_norm_w && d_norm_b), "hgt_update_backward: LayerNorm gradients need output buffers");
-  HGT_CHECK_CUDA(cudaMemsetAsync(d_skip, 0, (size_t)num_types * sizeof(float), st));
+  if (skip) HGT_CHECK_CUDA(cudaMemsetAsync(d_skip, 0, (size_t)num_types * sizeof(float), st));
   if (norm_w) {
     HGT_CHECK_CUDA(cudaMemsetAsync(d_norm_w, 0, (size_t)num_types * d * sizeof(float), st));
     HGT_CHECK_CUDA(cudaMemsetAsync(d_norm_b, 0, (size_t)num_types * d * sizeof(float), st));

@@ -4,7 +4,8 @@ stack of ``GeneralConv('hgt')`` layers — SURVEY.md §8(f) rank 1.  Parameter n
 
 The adapter is the same "per-type linear dispatch" as inside HGTConv and runs through the same C-ABI grouped GEMM
 (``hgt_typed_linear``: tcgen05 when in_dim >= 64 and n_hid % 16 == 0, fp32 SIMT otherwise); every layer shares
-the one cached graph plan.  Inference (no_grad) only; under autograd the adapter falls back to per-type F.linear.
+the one cached graph plan.  Under autograd the adapter uses the same GEMM with its native backward
+(``autograd._TypedLinear``).
 """
 import torch
 import torch.nn as nn
@@ -37,6 +38,18 @@ class GNN(nn.Module):
             if isinstance(gc.base_conv, HGTConv) and type(gc.base_conv) is HGTConv:
                 gc.base_conv.emit_split = True
 
+    def _adapter_table(self, plan, dev):
+        key = ("adapter", self.in_dim, self.n_hid)
+        table = plan._layer_tables.get(key)
+        if table is None:
+            groups, cblocks = [], []
+            for t in range(self.num_types):
+                if plan.type_count[t]:
+                    groups.append((plan.type_row0[t], plan.type_count[t], t * self.n_hid, 1, len(cblocks), 1))
+                    cblocks.append((plan.type_row0[t] * self.n_hid, self.n_hid))
+            table = plan._layer_tables[key] = _plan._pack_groups(groups, cblocks, dev)
+        return table
+
     def _adapter_cuda(self, node_feature, node_type, edge_index, edge_type, edge_time):
         conv0 = self.gcs[0].base_conv
         T = self.num_types
@@ -49,15 +62,7 @@ class GNN(nn.Module):
             xs = torch.empty_like(x)
             _lib.call("hgt_gather_rows", x.data_ptr(), plan.perm.data_ptr(), N, self.in_dim, xs.data_ptr(), st)
             x = xs
-        key = ("adapter", self.in_dim, self.n_hid)
-        table = plan._layer_tables.get(key)
-        if table is None:
-            groups, cblocks = [], []
-            for t in range(T):
-                if plan.type_count[t]:
-                    groups.append((plan.type_row0[t], plan.type_count[t], t * self.n_hid, 1, len(cblocks), 1))
-                    cblocks.append((plan.type_row0[t] * self.n_hid, self.n_hid))
-            table = plan._layer_tables[key] = _plan._pack_groups(groups, cblocks, dev)
+        table = self._adapter_table(plan, dev)
         w_cat = torch.empty((T * self.n_hid, self.in_dim), dtype=torch.float32, device=dev)
         b_cat = torch.empty(T * self.n_hid, dtype=torch.float32, device=dev)
         wp = conv0._ptrs("adapt_w", [l.weight for l in self.adapt_ws], dev)
@@ -72,17 +77,35 @@ class GNN(nn.Module):
             res = res.index_select(0, plan.rank.long())
         return res
 
+    def _adapter_autograd(self, node_feature, node_type, edge_index, edge_type, edge_time):
+        """Training path of the adapter: the same grouped GEMM with its native backward (autograd._TypedLinear)."""
+        from .autograd import typed_linear
+        conv0 = self.gcs[0].base_conv
+        T = self.num_types
+        plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if conv0.use_RTE else None, T,
+                              conv0.num_relations)
+        N = plan.n_nodes
+        x = node_feature if plan.sorted_types else node_feature.index_select(0, plan.perm.long())
+        table = self._adapter_table(plan, node_feature.device)
+        w_cat = torch.cat([l.weight for l in self.adapt_ws], 0)
+        b_cat = torch.cat([l.bias for l in self.adapt_ws], 0)
+        n_known = plan.type_row0[T]
+        res = typed_linear(x, w_cat, b_cat, table, self.n_hid, N * self.n_hid, conv0.linear_impl, 0,
+                           ((n_known * self.n_hid, N * self.n_hid),)).view(N, self.n_hid)
+        res = torch.cat([torch.tanh(res[:n_known]), res[n_known:]], 0) if n_known < N else torch.tanh(res)   # model.py:75
+        if not plan.sorted_types:
+            res = res.index_select(0, plan.rank.long())
+        return res
+
     def forward(self, node_feature, node_type, edge_time, edge_index, edge_type):
         grad = torch.is_grad_enabled() and (node_feature.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if node_feature.is_cuda and not grad and isinstance(self.gcs[0].base_conv, HGTConv):
-            res = self._adapter_cuda(node_feature, node_type, edge_index, edge_type, edge_time)
+        if not node_feature.is_cuda:
+            raise _lib.HgtError("pyhgt_b200.GNN runs on CUDA tensors only (got %s): there is no CPU fallback"
+                                % node_feature.device)
+        if grad:
+            res = self._adapter_autograd(node_feature, node_type, edge_index, edge_type, edge_time)
         else:
-            res = torch.zeros(node_feature.size(0), self.n_hid, device=node_feature.device)
-            for t_id in range(self.num_types):
-                idx = (node_type == int(t_id))
-                if idx.sum() == 0:
-                    continue
-                res[idx] = torch.tanh(self.adapt_ws[t_id](node_feature[idx]))
+            res = self._adapter_cuda(node_feature, node_type, edge_index, edge_type, edge_time)
         meta_xs = self.drop(res)
         del res
         for gc in self.gcs:
