@@ -194,7 +194,7 @@ class HGTConv(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _forward_fused(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att,
-                       active_per_type=None, out_map=None, out_rows=None, x_split=None):
+                       active_per_type=None, out_map=None, out_rows=None, x_split=None, kv_runs=None):
         """Inference through the single entry point hgt_conv_forward (csrc/layer.cu).  The argument block is cached per
         (plan tables, parameter locations); per call only the data pointers change."""
         dev = node_inp.device
@@ -203,7 +203,7 @@ class HGTConv(nn.Module):
         N, E = plan.n_nodes, plan.n_edges
         if node_inp.shape[0] != N:
             raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
-        lt = _plan.layer_tables(plan, d_in, d, active_per_type)
+        lt = _plan.layer_tables(plan, d_in, d, active_per_type, kv_runs)
         tabs = [self._ptrs("wq", [l.weight for l in self.q_linears], dev),
                 self._ptrs("bq", [l.bias for l in self.q_linears], dev),
                 self._ptrs("wk", [l.weight for l in self.k_linears], dev),
@@ -284,15 +284,15 @@ class HGTConv(nn.Module):
         return out, att, None
 
     def _forward_impl(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save,
-                      active_per_type=None, out_map=None, out_rows=None, x_split=None):
+                      active_per_type=None, out_map=None, out_rows=None, x_split=None, kv_runs=None):
         """out_map / out_rows (sharded runs): int32 [N] map from rank-order row to output row and the number of output
         rows; rows that are not active (halo sources) are never written, so the output holds exactly the owned rows."""
         if (self.fused_call and not save and HGTConv.event_sink is None and type(self)._has_skip
                 and not (self.training and self.drop.p > 0)):
             return self._forward_fused(node_inp, node_type, edge_index, edge_type, edge_time, want_att,
-                                       active_per_type, out_map, out_rows, x_split)
+                                       active_per_type, out_map, out_rows, x_split, kv_runs)
         c = self._core(node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
-                       gelu_before_a=True, x_split=x_split)
+                       gelu_before_a=True, x_split=x_split, kv_runs=kv_runs)
         plan, lt, o, x_sorted, N, d, T, st = c["plan"], c["lt"], c["o"], c["x_sorted"], c["N"], c["d"], c["T"], c["st"]
         f32 = dict(dtype=torch.float32, device=o.device)
         norm_w = norm_b = None
@@ -320,7 +320,7 @@ class HGTConv(nn.Module):
         return out, c["att"], (c if save else None)
 
     def _core(self, node_inp, node_type, edge_index, edge_type, edge_time, want_att, save, active_per_type,
-              gelu_before_a, x_split=None):
+              gelu_before_a, x_split=None, kv_runs=None):
         """Everything up to and including the typed a_linear: plan, weight fold, typed projections, fused edge kernel
         (gelu fused iff gelu_before_a and not save), a_linears.  Returns a dict of the intermediates."""
         dev = node_inp.device
@@ -331,7 +331,7 @@ class HGTConv(nn.Module):
         N, E, P = plan.n_nodes, plan.n_edges, plan.n_pairs
         if node_inp.shape[0] != N:
             raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
-        lt = _plan.layer_tables(plan, d_in, d, active_per_type)
+        lt = _plan.layer_tables(plan, d_in, d, active_per_type, kv_runs)
         f32 = dict(dtype=torch.float32, device=dev)
         x = node_inp.contiguous()
         if x_split is None and plan.sorted_types and self.linear_impl in (0, 2):

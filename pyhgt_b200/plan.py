@@ -259,10 +259,13 @@ def _pack_groups(groups, cblocks, dev):
     return tab
 
 
-def layer_tables(plan, d_in, d_out, active=None):
+def layer_tables(plan, d_in, d_out, active=None, kv_runs=None):
     """`active[t]` (sharded runs): only the first active[t] nodes of type t (in rank order) are destinations
-    that need Q / a_linear / update; the rest of the type (halo sources) only get K'/V' rows."""
-    key = (d_in, d_out, None if active is None else tuple(active))
+    that need Q / a_linear / update; the rest of the type (halo sources) only get K'/V' rows.
+    `kv_runs` (sharded runs): (((type, relation), ((row0, row1), ...)), ...) — type-relative row ranges whose K'/V' rows
+    some local edge reads; the projection then covers those ranges only (the other rows of the table are never
+    gathered and stay unwritten)."""
+    key = (d_in, d_out, None if active is None else tuple(active), kv_runs)
     hit = plan._layer_tables.get(key)
     if hit is not None:
         return hit
@@ -302,6 +305,25 @@ def layer_tables(plan, d_in, d_out, active=None):
                 cblocks.append((base, 2 * d_out))
                 cblocks.append((base + d_out, 2 * d_out))
             groups.append((plan.type_row0[t] + a, m - a, q_row0[t] + d_out, 2 * len(pairs_of_type[t]), first, 1))
+    if kv_runs is not None:
+        # per-pair compaction: a Q group over the active prefix, and one K'/V' group per needed row range of every pair
+        runs = dict(kv_runs)
+        g2, c2 = [], []
+        for t in range(T):
+            if plan.type_count[t] and act[t] > 0:
+                g2.append((plan.type_row0[t], act[t], q_row0[t], 1, len(c2), 1))
+                c2.append((q_off + plan.type_row0[t] * d_out, d_out))
+        for p, (s_, r_) in enumerate(plan.pairs):
+            for (r0, r1) in runs.get((s_, r_), ()):
+                r1 = min(int(r1), plan.type_count[s_])
+                if r1 <= r0:
+                    continue
+                base = kv_off + (plan.pair_row0[p] + int(r0)) * 2 * d_out
+                g2.append((plan.type_row0[s_] + int(r0), r1 - int(r0), cat_row0[p], 2, len(c2), 1))
+                c2.append((base, 2 * d_out))
+                c2.append((base + d_out, 2 * d_out))
+        if len(g2) <= 64 and all((s_, r_) in runs for (s_, r_) in plan.pairs):
+            groups, cblocks = g2, c2
     proj = _pack_groups(groups, cblocks, dev)
     groups, cblocks = [], []
     for p in range(P):

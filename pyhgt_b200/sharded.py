@@ -94,6 +94,7 @@ class ShardedGraph:
     halo_mode: str = "auto"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer
                                       # memory; "auto": p2p on CUDA when symmetric memory works, else nccl
     _symm: object = None
+    kv_runs: tuple = None             # (((type, relation), ((row0, row1), ...)), ...) type-relative local rows that need K'/V'
 
     @staticmethod
     def build(node_type, edge_index, edge_type, edge_time, num_types, num_relations, rank, world, device,
@@ -121,11 +122,44 @@ class ShardedGraph:
         halo = srcs[owner[srcs] != rank]
         halo = halo[torch.argsort(owner[halo] * n + halo)]                   # arrival order: by owner, then id
         n_owned, n_halo = int(owned.numel()), int(halo.numel())
-        # local order: per type [owned | halo]  => node_type is sorted, Q/update act on a prefix of every type
+        # local order: per type [owned | halo]  => node_type is sorted, Q/update act on a prefix of every type.
+        # Inside both parts the nodes are ordered by WHICH relations they feed on this rank (bit r of `rel_mask`: the
+        # node is the source of a local edge of relation r), owned ascending / halo descending, so that the rows a
+        # <source type, relation> pair really needs form a few contiguous runs: K'/V' are projected for those runs only
+        # (kv_runs) instead of for every local node of the type.
         cat_ids = torch.cat([owned, halo])                                   # order of concat([x_own, recv])
         is_halo = torch.cat([torch.zeros(n_owned, dtype=torch.int64), torch.ones(n_halo, dtype=torch.int64)])
-        order = torch.argsort(tkey[cat_ids] * 2 + is_halo, stable=True)
+        rel_sel = edge_type[e_sel]
+        rel_mask = torch.zeros(n, dtype=torch.int64)
+        compact = num_relations <= 16
+        if compact:
+            for r in range(num_relations):
+                sr = src[rel_sel == r]
+                rel_mask[sr] = rel_mask[sr] | (1 << r)
+        n_masks = 1 << min(num_relations, 16)
+        mk = rel_mask[cat_ids]
+        sub = torch.where(is_halo == 1, n_masks - 1 - mk, mk)
+        order = torch.argsort((tkey[cat_ids] * 2 + is_halo) * n_masks + sub, stable=True)
         local_global = cat_ids[order]
+        # runs of local rows (type-relative) whose mask contains relation r, per (type, relation)
+        kv_runs = None
+        if compact:
+            kv_runs = {}
+            lt_ = tkey[local_global]
+            lm = rel_mask[local_global]
+            for t in range(num_types):
+                rows_t = (lt_ == t).nonzero(as_tuple=True)[0]
+                if rows_t.numel() == 0:
+                    continue
+                mt = lm[rows_t]
+                for r in range(num_relations):
+                    has = ((mt >> r) & 1).to(torch.int8)
+                    if int(has.sum()) == 0:
+                        continue
+                    edge_ = torch.diff(torch.cat([torch.zeros(1, dtype=torch.int8), has, torch.zeros(1, dtype=torch.int8)]))
+                    starts = (edge_ == 1).nonzero(as_tuple=True)[0].tolist()
+                    ends = (edge_ == -1).nonzero(as_tuple=True)[0].tolist()
+                    kv_runs[(t, r)] = tuple(zip(starts, ends))
         local_of = torch.full((n,), -1, dtype=torch.int64)
         local_of[local_global] = torch.arange(local_global.numel())
         ei_local = torch.stack([local_of[src], local_of[dst]])
@@ -155,7 +189,8 @@ class ShardedGraph:
                             pull_rank=owner[local_global].to(torch.int32).to(device),
                             pull_row=owned_pos[local_global].to(torch.int32).to(device),
                             own_rows=local_of[owned].to(device), active_per_type=active, max_owned=max_owned,
-                            num_types=num_types, num_relations=num_relations, group=group, halo_mode=mode)
+                            num_types=num_types, num_relations=num_relations, group=group, halo_mode=mode,
+                            kv_runs=None if kv_runs is None else tuple(sorted(kv_runs.items())))
 
     # --------------------------------------------------------------------------------------------
     def _gather(self, src, idx32, n_rows):
@@ -285,7 +320,7 @@ class ShardedGraph:
             out, att, _ = conv._forward_impl(x_local, l_nt, l_ei, l_et,
                                              l_tm if conv.use_RTE else None, want_att=False, save=False,
                                              active_per_type=self.active_per_type, out_map=self._out_map,
-                                             out_rows=self.n_owned, x_split=x_split)
+                                             out_rows=self.n_owned, x_split=x_split, kv_runs=self.kv_runs)
             return out
         out, att, _ = conv._forward_impl(x_local, l_nt, l_ei, l_et,
                                          l_tm if conv.use_RTE else None, want_att=False, save=False,

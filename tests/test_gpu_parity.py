@@ -311,6 +311,22 @@ def test_sharded_local_forward_matches_full_graph(world):
                                          want_att=False, save=False, active_per_type=sh.active_per_type,
                                          out_map=om, out_rows=sh.n_owned)
         _close(out2, full[sh.owned_global], "rank %d/%d direct owned-order output" % (rank, world), atol=1e-5)
+        # per-pair compaction (what ShardedGraph.forward ships): K'/V' projected only for the row ranges local edges read
+        assert sh.kv_runs is not None
+        from pyhgt_b200 import plan as P
+        pl = P.get_plan(sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time, 3, 4)
+        full_rows = sum(pl.type_count[s_] for (s_, _) in pl.pairs)
+        run_rows = sum(r1 - r0 for (key, rs) in sh.kv_runs if key in pl.pairs for (r0, r1) in rs)
+        assert run_rows < full_rows
+        for fused in (True, False):
+            m.fused_call = fused
+            with torch.no_grad():
+                out3, _, _ = m._forward_impl(x_local, sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time,
+                                             want_att=False, save=False, active_per_type=sh.active_per_type,
+                                             out_map=om, out_rows=sh.n_owned, kv_runs=sh.kv_runs)
+            _close(out3, full[sh.owned_global], "rank %d/%d compacted projection (fused %s)" % (rank, world, fused),
+                   atol=1e-5)
+        m.fused_call = True
 
 
 @pytest.mark.parametrize("name", ["c1_rte", "rand_t3r4_dk4"])
