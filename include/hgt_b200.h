@@ -85,7 +85,10 @@ int hgt_plan_edges_fill(const int64_t* edge_index, const int64_t* edge_type, con
  *   the second field is -(partial_slot+1) < 0 and [edge_begin, edge_end) is a sub-range of its segment.
  *   hubs [max_hubs,4] int32 = {dst, first partial slot, pieces, 0} for every split destination;
  *   n_tiles [3] int32 = {number of tiles, number of split (partial) tiles, number of hubs}.
- * Synchronises the stream (returns the counts to the host through h_n_tiles[3]). */
+ * Synchronises the stream (returns the counts to the host through h_n_tiles[3]) — unless h_n_tiles is NULL: then
+ * nothing is read back or synchronised, the counts stay in d_n_tiles (pass it to the edge kernels as d_tile_counts)
+ * and the caller sizes with the bounds  max_tiles >= (2E+N)/(2*target_edges) + 3*(E/split_edges) + 16,
+ * max_hubs >= E/split_edges + 1,  split pieces <= 2*(E/split_edges) + 1. */
 int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges,
                    int32_t target_edges, int32_t split_edges,
                    int32_t* tiles, int64_t max_tiles, int32_t* hubs, int64_t max_hubs,
@@ -184,7 +187,10 @@ int hgt_typed_linear_presplit(const void* a_hi, const void* a_lo, const float* W
  *  stats_out [N, 2H] per-destination (max, sum) per head, or NULL (kept for the backward pass)
  *  g_hi / g_lo [N, d] bf16 or NULL: the same result as a bf16 hi/lo split (x = hi + lo to ~2^-17), i.e. the
  *           pre-split A operand of hgt_typed_linear_presplit; agg_out may then be NULL.  Needs d % 8 == 0.
- *  variant: 0 = auto, 1 = direct register gather (LDG), 2 = bulk-async-copy shared-memory ring (TMA) */
+ *  variant: 0 = auto, 1 = direct register gather (LDG), 2 = bulk-async-copy shared-memory ring (TMA)
+ *  d_tile_counts: NULL, or the device counts {n_tiles, n_split, n_hubs} hgt_plan_tiles wrote in its sync-free mode; then
+ *           n_tiles / n_split_tiles / n_hubs are the UPPER BOUNDS the arrays were sized with and the kernels read the
+ *           true counts from the device (no host read-back between plan build and layer). */
 int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_t n_heads, size_t* out_bytes);
 int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
@@ -192,7 +198,8 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      const int32_t* hubs, int32_t n_hubs,
                      int64_t n_nodes, int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu,
                      float* agg_out, float* att_out, float* stats_out, void* g_hi, void* g_lo,
-                     void* workspace, size_t workspace_bytes, int32_t variant, void* stream);
+                     void* workspace, size_t workspace_bytes, int32_t variant, const int32_t* d_tile_counts,
+                     void* stream);
 
 /* Backward of hgt_edge_forward (training; the reference differentiates the same ops with autograd,
  * OAG/train_paper_field.py:249).  Inputs: the forward's q / kv / kvr tables, its un-activated output
@@ -204,7 +211,8 @@ int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const f
                       const float* stats, const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
                       const int32_t* tiles, int32_t n_tiles, int64_t n_nodes, int32_t d, int32_t n_heads,
                       int64_t kv_rows_total, int64_t kvr_rows_total,
-                      float* dq, float* dkv, float* dkvr, void* workspace, size_t workspace_bytes, void* stream);
+                      float* dq, float* dkv, float* dkvr, void* workspace, size_t workspace_bytes,
+                      const int32_t* d_tile_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward of the typed linears (training path).  For the group / column-block tables of the forward call:
@@ -298,6 +306,7 @@ typedef struct {
   const int32_t* csr_eid;
   const int32_t* tiles;
   const int32_t* hubs;
+  const int32_t* d_tile_counts; /* NULL, or device {n_tiles, n_split, n_hubs}: n_tiles/n_split/n_hubs above are bounds */
   const int32_t* pair_type;
   const int32_t* pair_rel;
   const int32_t* cat_row0;

@@ -35,11 +35,11 @@ SIGNATURES = {
     "hgt_typed_linear": [_p, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _sz, _p],
     "hgt_edge_workspace_bytes": [_i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p,
-                         _p, _p, _p, _p, _sz, _i32, _p],
+                         _p, _p, _p, _p, _sz, _i32, _p, _p],
     "hgt_typed_linear_presplit_workspace_bytes": [_p, _i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_typed_linear_presplit": [_p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p],
     "hgt_edge_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _sz,
-                          _p],
+                          _p, _p],
     "hgt_typed_linear_bwd_workspace_bytes": [_p, _i32, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_typed_linear_bwd": [_p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p,
                              _i32, _p, _sz, _p],
@@ -59,7 +59,7 @@ class ConvArgs(ctypes.Structure):
     _I32 = ["num_types", "num_relations", "n_heads", "d_in", "d_out", "n_pairs", "use_rte", "use_norm", "edge_variant",
             "linear_impl", "n_tiles", "n_split", "n_hubs", "n_proj_groups", "n_rte_groups", "n_upd_groups"]
     _PTR = ["perm", "type_row0", "type_active", "out_map", "row_ptr", "kv_row", "rte_row", "csr_eid", "tiles", "hubs",
-            "pair_type", "pair_rel", "cat_row0", "q_row0",
+            "d_tile_counts", "pair_type", "pair_rel", "cat_row0", "q_row0",
             "proj_groups", "h_proj_groups", "proj_cblocks", "rte_groups", "h_rte_groups", "rte_cblocks",
             "rt_groups", "h_rt_groups", "rt_cblocks", "upd_groups", "h_upd_groups", "upd_cblocks",
             "wq", "bq", "wk", "bk", "wv", "bv", "wa", "ba", "norm_w", "norm_b",

@@ -126,7 +126,7 @@ class _EdgeAttention(torch.autograd.Function):
                   plan.kv_row.data_ptr(), None if kvr is None else plan.rte_row.data_ptr(), plan.csr_eid.data_ptr(),
                   plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, plan.n_edges, d,
                   n_heads, 0, agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
-                  variant, _stream())
+                  variant, _lib.ptr(plan.tile_counts_dev), _stream())
         ctx.plan, ctx.lt, ctx.d, ctx.n_heads, ctx.has_kvr = plan, lt, d, n_heads, kvr is not None
         ctx.save_for_backward(proj, kvr, agg, stats)
         if att is not None:
@@ -152,7 +152,8 @@ class _EdgeAttention(torch.autograd.Function):
                   stats.data_ptr(), plan.row_ptr.data_ptr(), plan.kv_row.data_ptr(),
                   None if kvr is None else plan.rte_row.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, N, d, H,
                   plan.kv_rows + 1, 0 if kvr is None else kvr.numel() // (2 * d),
-                  dq.data_ptr(), dkv.data_ptr(), _lib.ptr(dkvr), ws.data_ptr(), ws.numel(), _stream())
+                  dq.data_ptr(), dkv.data_ptr(), _lib.ptr(dkvr), ws.data_ptr(), ws.numel(),
+                  _lib.ptr(plan.tile_counts_dev), _stream())
         return dproj, dkvr, None, None, None, None, None, None
 
 

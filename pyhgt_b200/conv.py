@@ -233,6 +233,7 @@ class HGTConv(nn.Module):
             a.row_ptr, a.kv_row = plan.row_ptr.data_ptr(), plan.kv_row.data_ptr()
             a.rte_row = plan.rte_row.data_ptr() if self.use_RTE else None
             a.csr_eid, a.tiles, a.hubs = plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.hubs.data_ptr()
+            a.d_tile_counts = _lib.ptr(plan.tile_counts_dev)
             a.pair_type, a.pair_rel = plan.pair_type_dev.data_ptr(), plan.pair_rel_dev.data_ptr()
             a.cat_row0, a.q_row0 = lt.cat_row0_dev.data_ptr(), lt.q_row0_dev.data_ptr()
             for name, tab in (("proj", lt.proj_groups), ("rte", lt.rte_groups), ("rt", lt.rt_group), ("upd", lt.upd_groups)):
@@ -407,7 +408,7 @@ class HGTConv(nn.Module):
                       plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split,
                       plan.hubs.data_ptr(), plan.n_hubs, N, E, d, H, 1 if (gelu_before_a and not save) else 0,
                       _lib.ptr(g_act), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(g_hi), _lib.ptr(g_lo), ws.data_ptr(),
-                      ws.numel(), self.edge_variant, st)
+                      ws.numel(), self.edge_variant, _lib.ptr(plan.tile_counts_dev), st)
 
         # 4. typed output linear (conv.py:125 / conv.py:261)
         agg = None

@@ -34,7 +34,8 @@ struct EdgeParams {
   const int32_t* rte_row;
   const int32_t* csr_eid;
   const int32_t* tiles;
-  int32_t n_tiles;
+  int32_t n_tiles;           // exact count, or an upper bound when d_counts is given
+  const int32_t* d_counts;   // optional device {n_tiles, n_split, n_hubs} written by hgt_plan_tiles (sync-free plans)
   int32_t d, H, DK, LPH, lph_shift;
   int32_t apply_gelu;
   float* agg_out;            // nullptr when only the split bf16 copy is wanted
@@ -202,11 +203,12 @@ k_edge_fwd_ldg(EdgeParams p) {
 #pragma unroll
   for (int t = 0; t < NCH; ++t) offs[t] = lm.off<VEC>(t);
 
+  const int n_tiles = p.d_counts ? p.d_counts[0] : p.n_tiles;
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= p.n_tiles) break;
+    if (tile >= n_tiles) break;
     const int4 tl = reinterpret_cast<const int4*>(p.tiles)[tile];
     const bool split = tl.y < 0;
     const int d_begin = tl.x, d_end = split ? tl.x + 1 : tl.y;
@@ -369,11 +371,12 @@ k_edge_fwd_tma(EdgeParams p) {
 
   uint32_t it = 0;   // rows consumed so far by this warp (slot = it % S, parity = (it / S) & 1)
 
+  const int n_tiles = p.d_counts ? p.d_counts[0] : p.n_tiles;
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= p.n_tiles) break;
+    if (tile >= n_tiles) break;
     const int4 tl = reinterpret_cast<const int4*>(p.tiles)[tile];
     const bool split = tl.y < 0;
     const int d_begin = tl.x, d_end = split ? tl.x + 1 : tl.y;
@@ -486,7 +489,8 @@ k_edge_fwd_tma(EdgeParams p) {
 constexpr int kMergeThreads = 1024;
 
 __global__ void __launch_bounds__(kMergeThreads)
-k_merge_partials(EdgeParams p, const int32_t* __restrict__ hubs, int n_hubs) {
+k_merge_partials(EdgeParams p, const int32_t* __restrict__ hubs, int n_hubs_host) {
+  const int n_hubs = p.d_counts ? p.d_counts[2] : n_hubs_host;
   __shared__ float s_M[32], s_L[32], s_inv[32];
   __shared__ float s_red[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,8 +563,12 @@ int launch_variant(const EdgeParams& p, int variant, int grid, size_t smem, cuda
   if (variant == 1) {
     k_edge_fwd_ldg<VEC, NCH><<<grid, kCtaThreads, 0, st>>>(p);
   } else {
-    HGT_CHECK_CUDA(cudaFuncSetAttribute(k_edge_fwd_tma<VEC, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    static size_t configured = 0;            // per instantiation: raise the dynamic shared-memory limit once, not per launch
+    if (smem > configured) {
+      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_edge_fwd_tma<VEC, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+      configured = smem;
+    }
     k_edge_fwd_tma<VEC, NCH><<<grid, kCtaThreads, smem, st>>>(p);
   }
   HGT_LAUNCH_CHECK();
@@ -593,7 +601,8 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
                                 int32_t n_hubs, int64_t n_nodes,
                                 int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu, float* agg_out,
                                 float* att_out, float* stats_out, void* g_hi, void* g_lo, void* workspace,
-                                size_t workspace_bytes, int32_t variant, void* stream_) {
+                                size_t workspace_bytes, int32_t variant, const int32_t* d_tile_counts,
+                                void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   (void)n_edges;
   HGT_REQUIRE(n_heads >= 1 && n_heads <= 32, "hgt_edge_forward: n_heads=%d unsupported (1..32)", n_heads);
@@ -609,7 +618,7 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
 
   EdgeParams p;
   p.q = q; p.kv = kv; p.kvr = kvr; p.row_ptr = row_ptr; p.kv_row = kv_row; p.rte_row = rte_row;
-  p.csr_eid = csr_eid; p.tiles = tiles; p.n_tiles = n_tiles; p.d = d; p.H = n_heads; p.DK = d / n_heads;
+  p.csr_eid = csr_eid; p.tiles = tiles; p.n_tiles = n_tiles; p.d_counts = d_tile_counts; p.d = d; p.H = n_heads; p.DK = d / n_heads;
   int hp = 1, shift = 5;
   while (hp < n_heads) hp <<= 1;
   p.LPH = 32 / hp;

@@ -27,6 +27,7 @@ struct BwdParams {
   const int32_t* rte_row;
   const int32_t* tiles;
   int32_t n_tiles;
+  const int32_t* d_counts;   // optional device {n_tiles, ...} (sync-free plans): n_tiles is then an upper bound
   int32_t d, H, DK, LPH, lph_shift;
   float* dq;                 // [N, d]   zero-initialised by hgt_edge_backward
   float* dkv;                // [rows+1, 2d] zero-initialised
@@ -79,11 +80,12 @@ k_edge_bwd(BwdParams p) {
   const int64_t row_stride = 2 * (int64_t)p.d;
   const bool rte = p.kvr != nullptr;
 
+  const int n_tiles = p.d_counts ? p.d_counts[0] : p.n_tiles;
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= p.n_tiles) break;
+    if (tile >= n_tiles) break;
     const int4 tl = reinterpret_cast<const int4*>(p.tiles)[tile];
     const bool split = tl.y < 0;
     const int d_begin = tl.x, d_end = split ? tl.x + 1 : tl.y;
@@ -201,7 +203,7 @@ extern "C" int hgt_edge_backward(const float* q, const float* kv, const float* k
                                  const int32_t* kv_row, const int32_t* rte_row, const int32_t* tiles, int32_t n_tiles,
                                  int64_t n_nodes, int32_t d, int32_t n_heads, int64_t kv_rows_total,
                                  int64_t kvr_rows_total, float* dq, float* dkv, float* dkvr,
-                                 void* workspace, size_t workspace_bytes, void* stream_) {
+                                 void* workspace, size_t workspace_bytes, const int32_t* d_tile_counts, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(n_heads >= 1 && n_heads <= 32 && d % n_heads == 0, "hgt_edge_backward: bad d=%d / n_heads=%d", d, n_heads);
   HGT_REQUIRE((kvr != nullptr) == (rte_row != nullptr) && (kvr != nullptr) == (dkvr != nullptr),
@@ -215,7 +217,7 @@ extern "C" int hgt_edge_backward(const float* q, const float* kv, const float* k
   if (n_nodes == 0 || n_tiles == 0) return 0;
   BwdParams p;
   p.q = q; p.kv = kv; p.kvr = kvr; p.agg = agg; p.dagg = dagg; p.stats = stats; p.row_ptr = row_ptr;
-  p.kv_row = kv_row; p.rte_row = rte_row; p.tiles = tiles; p.n_tiles = n_tiles; p.d = d; p.H = n_heads;
+  p.kv_row = kv_row; p.rte_row = rte_row; p.tiles = tiles; p.n_tiles = n_tiles; p.d_counts = d_tile_counts; p.d = d; p.H = n_heads;
   p.DK = d / n_heads;
   int hp = 1;
   while (hp < n_heads) hp <<= 1;

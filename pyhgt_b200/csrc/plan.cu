@@ -374,7 +374,7 @@ extern "C" int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n
                               size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(target_edges >= 1 && split_edges >= 1, "hgt_plan_tiles: bad tile parameters");
-  h_n_tiles[0] = h_n_tiles[1] = h_n_tiles[2] = 0;
+  if (h_n_tiles) h_n_tiles[0] = h_n_tiles[1] = h_n_tiles[2] = 0;
   HGT_CHECK_CUDA(cudaMemsetAsync(d_n_tiles, 0, 3 * sizeof(int32_t), st));
   if (n_nodes == 0) return 0;
   int tc = 2 * target_edges;
@@ -391,6 +391,15 @@ extern "C" int hgt_plan_tiles(const int32_t* row_ptr, int64_t n_nodes, int64_t n
   k_tile_write<<<blocks_for(n_nodes + 1), kThreads, 0, st>>>(row_ptr, n_nodes, tc, split_edges, packed, tiles,
                                                              max_tiles, d_n_tiles, hubs, max_hubs);
   HGT_LAUNCH_CHECK();
+  if (h_n_tiles == nullptr) {
+    // sync-free mode: the counts stay on the device (the edge kernels read them through d_tile_counts); tile slots past
+    // max_tiles are never written (k_tile_write clamps), so callers size max_tiles / max_hubs with the documented bounds
+    if (max_tiles > 0) {
+      k_tile_close<<<blocks_for(max_tiles), kThreads, 0, st>>>(row_ptr, n_nodes, tiles, d_n_tiles);
+      HGT_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   HGT_CHECK_CUDA(cudaMemcpyAsync(h_n_tiles, d_n_tiles, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   HGT_CHECK_CUDA(cudaStreamSynchronize(st));
   HGT_REQUIRE(h_n_tiles[0] <= max_tiles, "hgt_plan_tiles: %d tiles exceed max_tiles=%lld", h_n_tiles[0],

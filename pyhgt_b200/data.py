@@ -6,7 +6,10 @@ Python loops that append one edge at a time (data.py:240-250); this version buil
 relation> block with one numpy conversion, so the output is IDENTICAL (same node order, same edge order, same dtypes:
 FloatTensor / LongTensor, row 0 of edge_index = source) at a fraction of the host time.  With ``device=`` the tensors
 are staged through pinned memory to the GPU and the destination-sorted CSR plan of the graph is built right away
-(``prebuild_plan``), so the first HGT layer does not pay for it.
+(``prebuild_plan``) WITHOUT any host synchronisation: the per-type node counts and the <source type, relation> pairs are
+known from the block structure of ``edge_list``, the tile counts stay on the device, and the
+range checks run on the host arrays — a new sampled graph per batch (OAG/train_paper_field.py:241) costs kernel
+launches only.
 """
 import numpy as np
 import torch
@@ -40,12 +43,14 @@ def to_torch(feature, time, edge_list, graph, device=None, prebuild_plan=False, 
     edge_dict['self'] = len(edge_dict)
 
     src_blocks, dst_blocks, typ_blocks = [], [], []
+    block_pairs = set()                                                   # <source type id, relation id> of every block
     for target_type in edge_list:                                         # data.py:240-250, same iteration order
         for source_type in edge_list[target_type]:
             for relation_type in edge_list[target_type][source_type]:
                 pairs = edge_list[target_type][source_type][relation_type]
                 if len(pairs) == 0:
                     continue
+                block_pairs.add((node_dict[source_type][1], edge_dict[relation_type]))
                 arr = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)   # [[target_ser, source_ser], ...]
                 dst_blocks.append(arr[:, 0] + node_dict[target_type][0])
                 src_blocks.append(arr[:, 1] + node_dict[source_type][0])
@@ -67,11 +72,21 @@ def to_torch(feature, time, edge_list, graph, device=None, prebuild_plan=False, 
     if device is not None:
         dev = torch.device(device)
         if dev.type == "cuda":
+            # The edges arrive grouped in <target type, source type, relation> blocks and the nodes type by type, so the
+            # host already knows the per-type counts and the <source type, relation> pairs: the plan is built from that
+            # (`host_meta`) with no device read-back, and the id / time ranges are validated here on the host arrays.
+            if prebuild_plan and edge_index.shape[1]:
+                if edge_index.min() < 0 or edge_index.max() >= node_num:
+                    raise IndexError("edge_list contains node indices outside the sampled feature lists")
+                if etime.min() < 0 or etime.max() >= 240:
+                    raise IndexError("edge_time contains values outside [0, 240) (RelTemporalEncoding table size)")
             out = [t.pin_memory().to(dev, non_blocking=True) for t in out]
             if prebuild_plan:
                 from . import plan as _plan
                 R = num_relations if num_relations is not None else len(edge_dict)
-                _plan.get_plan(out[1], out[3], out[4], out[2], len(types), R)
+                meta = {"type_count": [len(feature[t]) for t in types] + [0], "sorted": True,
+                        "pairs": sorted(block_pairs)}
+                _plan.get_plan(out[1], out[3], out[4], out[2], len(types), R, host_meta=meta)
         else:
             out = [t.to(dev) for t in out]
     node_feature, node_type, edge_time, edge_index, edge_type = out

@@ -58,7 +58,19 @@ class GraphPlan:
     n_hubs: int = 0
     pair_type_dev: torch.Tensor = None
     pair_rel_dev: torch.Tensor = None
+    tile_counts_dev: torch.Tensor = None   # sync-free plans: device {n_tiles, n_split, n_hubs}; the host fields are bounds
+    flags_dev: torch.Tensor = None         # sync-free plans: range-check flags left on the device (see check())
     _layer_tables: dict = field(default_factory=dict)
+
+    def check(self):
+        """Sync-free plans defer the index range checks: this reads the flags back (one host sync) and raises like
+        the synchronous build does."""
+        if self.flags_dev is not None:
+            f = self.flags_dev.cpu()
+            if int(f[0]) != 0:
+                raise IndexError("edge_index contains node ids outside [0, %d)" % self.n_nodes)
+            if self.has_time and int(f[1]) != 0:
+                raise IndexError("edge_time contains values outside [0, %d) (RelTemporalEncoding table size)" % RTE_MAX_LEN)
 
     @property
     def n_pairs(self):
@@ -110,20 +122,32 @@ def _as_i64(t, name, device):
     return t.contiguous()
 
 
-def get_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, use_cache=True):
+def _to_dev_async(arr, dev):
+    """Small host table -> device through pinned staging, without synchronising the stream."""
+    t = torch.from_numpy(arr)
+    if dev.type == "cuda":
+        return t.pin_memory().to(dev, non_blocking=True)
+    return t.to(dev)
+
+
+def get_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, use_cache=True, host_meta=None):
+    """`host_meta` (optional): what the host already knows about the graph — {"type_count": [T+1 ints], "sorted": bool,
+    "pairs": [(source_type, relation), ...]} — e.g. from `data.to_torch`, which builds the tensors from per-type blocks.
+    With it the plan is built WITHOUT any host read-back or stream synchronisation (sampled-subgraph regime: a new
+    graph every batch, OAG/train_paper_field.py:241); index range checks are then deferred (GraphPlan.check())."""
     tensors = (node_type, edge_index, edge_type, edge_time)
     extra = (num_types, num_relations)
     if use_cache:
         hit = _cache_lookup(tensors, extra)
         if hit is not None:
             return hit
-    plan = build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations)
+    plan = build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, host_meta)
     if use_cache:
         _cache_store(tensors, extra, plan)
     return plan
 
 
-def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations):
+def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, host_meta=None):
     dev = node_type.device
     if dev.type != "cuda":
         raise _lib.HgtError("pyhgt_b200 runs on CUDA tensors only (got %s); there is no CPU fallback" % dev)
@@ -147,27 +171,44 @@ def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relat
     _lib.call("hgt_plan_workspace_bytes", N, E, ctypes.byref(ws_bytes))
     ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
 
-    rank = torch.empty(max(N, 1), **i32)
-    perm = torch.empty(max(N, 1), **i32)
-    # one small buffer for everything the host has to read back: [type_count T+1 | sorted 1 | presence T*R | flags 4]
+    # one small buffer for everything the host may read back: [type_count T+1 | sorted 1 | presence T*R | flags 4]
     meta = torch.zeros(T + 1 + 1 + T * R + 4, **i32)
     type_count_d = meta[:T + 1]
     sorted_d = meta[T + 1:T + 2]
     presence_d = meta[T + 2:T + 2 + T * R]
     flags_d = meta[T + 2 + T * R:]
-    _lib.call("hgt_plan_nodes", nt.data_ptr(), N, T, rank.data_ptr(), perm.data_ptr(), type_count_d.data_ptr(),
-              sorted_d.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    sync_free = host_meta is not None
+    if sync_free and host_meta.get("sorted", False):
+        rank = torch.arange(max(N, 1), **i32)                  # type-contiguous layout (to_torch): identity order
+        perm = rank
+    else:
+        rank = torch.empty(max(N, 1), **i32)
+        perm = torch.empty(max(N, 1), **i32)
+        _lib.call("hgt_plan_nodes", nt.data_ptr(), N, T, rank.data_ptr(), perm.data_ptr(), type_count_d.data_ptr(),
+                  sorted_d.data_ptr(), ws.data_ptr(), ws.numel(), st)
     row_ptr = torch.empty(N + 1, **i32)
     csr_eid = torch.empty(max(E, 1), **i32)
     _lib.call("hgt_plan_edges_sort", ei.data_ptr(), et.data_ptr(), nt.data_ptr(), rank.data_ptr(), N, E, T, R,
               row_ptr.data_ptr(), csr_eid.data_ptr(), presence_d.data_ptr(), flags_d.data_ptr(), ws.data_ptr(),
               ws.numel(), st)
-    meta_h = meta.cpu().numpy()                       # the one host sync of the node/edge pass
-    type_count = [int(v) for v in meta_h[:T + 1]]
-    sorted_types = bool(meta_h[T + 1])
-    presence = meta_h[T + 2:T + 2 + T * R].reshape(T, R)
-    if meta_h[T + 2 + T * R] != 0:
-        raise IndexError("edge_index contains node ids outside [0, %d)" % N)
+    if sync_free:
+        type_count = [int(v) for v in host_meta["type_count"]]
+        if len(type_count) == T:
+            type_count.append(0)
+        if len(type_count) != T + 1 or sum(type_count) != N:
+            raise ValueError("host_meta['type_count'] must hold T (+1) counts summing to N=%d, got %s" % (N, type_count))
+        sorted_types = bool(host_meta.get("sorted", False))
+        presence = np.zeros((T, R), dtype=np.int32)
+        for (s_, r_) in host_meta["pairs"]:
+            if 0 <= s_ < T and 0 <= r_ < R:
+                presence[s_, r_] = 1
+    else:
+        meta_h = meta.cpu().numpy()                       # the one host sync of the node/edge pass
+        type_count = [int(v) for v in meta_h[:T + 1]]
+        sorted_types = bool(meta_h[T + 1])
+        presence = meta_h[T + 2:T + 2 + T * R].reshape(T, R)
+        if meta_h[T + 2 + T * R] != 0:
+            raise IndexError("edge_index contains node ids outside [0, %d)" % N)
 
     type_row0 = [0]
     for c in type_count:
@@ -188,7 +229,7 @@ def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relat
                             np.asarray(type_row0, dtype=np.int32),
                             np.asarray([p[0] for p in pairs] + [0], dtype=np.int32)[:max(P, 1)],
                             np.asarray([p[1] for p in pairs] + [0], dtype=np.int32)[:max(P, 1)]]).astype(np.int32)
-    small_d = torch.from_numpy(small).to(dev)
+    small_d = _to_dev_async(small, dev)
     o = 0
     pair_of_d = small_d[o:o + T * R]; o += T * R
     pair_row0_d = small_d[o:o + max(P, 1)]; o += max(P, 1)
@@ -207,19 +248,29 @@ def build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relat
     max_hubs = E // TILE_SPLIT_EDGES + 1
     hubs = torch.empty((max_hubs, 4), **i32)
     n_tiles_d = torch.zeros(4, **i32)
-    n_tiles_h = (ctypes.c_int32 * 4)()
-    _lib.call("hgt_plan_tiles", row_ptr.data_ptr(), N, E, TILE_TARGET_EDGES, TILE_SPLIT_EDGES, tiles.data_ptr(),
-              max_tiles, hubs.data_ptr(), max_hubs, n_tiles_d.data_ptr(), n_tiles_h, ws.data_ptr(), ws.numel(),
-              st)   # synchronises
-    if tm is not None and int(flags_d[1].item()) != 0:
-        raise IndexError("edge_time contains values outside [0, %d) (RelTemporalEncoding table size)" % RTE_MAX_LEN)
-    n_tiles, n_split, n_hubs = int(n_tiles_h[0]), int(n_tiles_h[1]), int(n_tiles_h[2])
+    if sync_free:
+        # counts stay on the device; the host-side fields become the bounds the arrays were sized with
+        _lib.call("hgt_plan_tiles", row_ptr.data_ptr(), N, E, TILE_TARGET_EDGES, TILE_SPLIT_EDGES, tiles.data_ptr(),
+                  max_tiles, hubs.data_ptr(), max_hubs, n_tiles_d.data_ptr(), None, ws.data_ptr(), ws.numel(), st)
+        has_hub = E > TILE_SPLIT_EDGES
+        n_tiles = max_tiles if N > 0 else 0
+        n_split = 2 * (E // TILE_SPLIT_EDGES) + 1 if has_hub else 0
+        n_hubs = max_hubs if has_hub else 0
+    else:
+        n_tiles_h = (ctypes.c_int32 * 4)()
+        _lib.call("hgt_plan_tiles", row_ptr.data_ptr(), N, E, TILE_TARGET_EDGES, TILE_SPLIT_EDGES, tiles.data_ptr(),
+                  max_tiles, hubs.data_ptr(), max_hubs, n_tiles_d.data_ptr(), n_tiles_h, ws.data_ptr(), ws.numel(),
+                  st)   # synchronises
+        if tm is not None and int(flags_d[1].item()) != 0:
+            raise IndexError("edge_time contains values outside [0, %d) (RelTemporalEncoding table size)" % RTE_MAX_LEN)
+        n_tiles, n_split, n_hubs = int(n_tiles_h[0]), int(n_tiles_h[1]), int(n_tiles_h[2])
     return GraphPlan(n_nodes=N, n_edges=E, num_types=T, num_relations=R, has_time=tm is not None,
                      sorted_types=sorted_types, rank=rank, perm=perm, type_count=type_count, type_row0=type_row0,
                      type_row0_dev=type_row0_d, row_ptr=row_ptr, csr_eid=csr_eid, kv_row=kv_row, rte_row=rte_row,
                      pairs=pairs, pair_row0=pair_row0, kv_rows=rows, tiles=tiles[:max(n_tiles, 1)],
                      n_tiles=n_tiles, n_split=n_split, hubs=hubs[:max(n_hubs, 1)], n_hubs=n_hubs,
-                     pair_type_dev=pair_type_d, pair_rel_dev=pair_rel_d)
+                     pair_type_dev=pair_type_d, pair_rel_dev=pair_rel_d,
+                     tile_counts_dev=n_tiles_d if sync_free else None, flags_dev=flags_d if sync_free else None)
 
 
 # ---- typed-linear descriptor tables (depend on the plan and on the layer's d_in / d_out) -------------
@@ -252,8 +303,8 @@ def _pack_groups(groups, cblocks, dev):
     c = np.zeros(max(len(cblocks), 1), dtype=_lib.LIN_CBLOCK_DTYPE)
     for i, t in enumerate(cblocks):
         c[i] = t
-    g_dev = torch.from_numpy(g.view(np.uint8).copy()).to(dev)
-    c_dev = torch.from_numpy(c.view(np.uint8).copy()).to(dev)
+    g_dev = _to_dev_async(g.view(np.uint8).copy(), dev)
+    c_dev = _to_dev_async(c.view(np.uint8).copy(), dev)
     tab = GroupTable((g_dev, g, len(groups), c_dev))
     tab.c_host = c                 # host copy of the column-block table (the backward pass sizes its launches with it)
     return tab
@@ -342,7 +393,7 @@ def layer_tables(plan, d_in, d_out, active=None, kv_runs=None):
         cblocks.append((plan.type_row0[t] * d_out, d_out))
     upd = _pack_groups(groups, cblocks, dev)
     rt_group = _pack_groups([(0, RTE_MAX_LEN, 0, 1, 0, 1)], [(0, d_in)], dev)
-    small = torch.tensor(q_row0 + (cat_row0 if P else [0]) + act, dtype=torch.int32).to(dev)
+    small = _to_dev_async(np.asarray(q_row0 + (cat_row0 if P else [0]) + act, dtype=np.int32), dev)
     lt = LayerTables(cat_rows=rows, q_row0=q_row0, cat_row0=cat_row0, q_row0_dev=small[:T],
                      cat_row0_dev=small[T:T + max(P, 1)],
                      type_active_dev=None if active is None else small[T + max(P, 1):], proj_groups=proj, rte_groups=rte, upd_groups=upd, rt_group=rt_group, q_off=q_off,

@@ -649,3 +649,85 @@ def test_module_saves_after_inference_forward(tmp_path):
     out2 = _run(m2, fx, dev)
     assert torch.equal(out, out2)
     _close(out2, fx["out"], "reloaded module")
+
+
+def test_sampled_subgraph_batch_runs_without_host_sync():
+    """The reference's training regime (OAG/train_paper_field.py:241): a NEW sampled graph every batch.  After a warm-up,
+    `to_torch(device=cuda, prebuild_plan=True)` + the layer run with NO host synchronisation (torch's sync debug mode
+    raises on any blocking call) and the sync-free plan gives the same result as the synchronous one and the oracle."""
+    import pyhgt_b200
+    from pyhgt_b200 import data as hdata, plan as P
+    from tests.test_data_ingest import _GraphStub
+    dev = _dev()
+    fx = load_golden("to_torch")
+    g = _GraphStub(fx["types"], fx["meta_graph"])
+    T = len(fx["types"])
+    d = fx["node_feature"].shape[1]
+    torch.manual_seed(0)
+    m = None
+
+    def batch():
+        nf, nt, etime, ei, et, node_dict, edge_dict = hdata.to_torch(fx["feature"], fx["time"], fx["edge_list"], g,
+                                                                    device=dev, prebuild_plan=True)
+        return nf, nt, etime, ei, et, len(edge_dict)
+
+    nf, nt, etime, ei, et, R = batch()
+    m = pyhgt_b200.HGTConv(d, d, T, R, 1, 0.2, True, False).to(dev).eval()
+    with torch.no_grad():
+        ref_sync = m(nf, nt, fx["edge_index"].to(dev), et)                 # synchronous plan (different tensor object)
+        out0 = m(nf, nt, ei, et, etime)                                   # warm-up of the sync-free path
+    torch.cuda.synchronize()
+    pl = P.get_plan(nt, ei, et, None, T, R)
+    assert pl.tile_counts_dev is not None                                 # the prebuilt plan is the sync-free one
+    pl.check()
+    P.clear_plan_cache()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        with torch.no_grad():
+            nf2, nt2, etime2, ei2, et2, _ = batch()                       # new tensors => new plan
+            out = m(nf2, nt2, ei2, et2, etime2)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.equal(out, out0)
+    _close(out, ref_sync, "sync-free plan vs synchronous plan", atol=1e-6)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref, _ = hgt_oracle.hgt_forward_ref_port(params, fx["node_feature"], fx["node_type"], fx["edge_index"],
+                                             fx["edge_type"], None, num_types=T, num_relations=R, n_heads=1,
+                                             use_RTE=False)
+    _close(out, ref, "sync-free batch vs oracle")
+
+
+def test_sync_free_plan_with_hubs_matches_synchronous_plan():
+    """Device-side tile counts (upper-bound grids, hub merge bounded on the device) on a graph with split hubs, forward
+    and backward."""
+    import pyhgt_b200
+    from pyhgt_b200 import plan as P
+    dev = _dev()
+    g = synth.make_random(600, 3000, 3, 2, seed=41, sorted_types=True)
+    gen = torch.Generator().manual_seed(4)
+    hub = torch.full((2500,), 17, dtype=torch.int64)
+    g.edge_index = torch.cat([g.edge_index, torch.stack([torch.randint(0, 600, (2500,), generator=gen), hub])], 1)
+    g.edge_type = torch.cat([g.edge_type, torch.randint(0, 2, (2500,), generator=gen)])
+    torch.manual_seed(1)
+    m = pyhgt_b200.HGTConv(64, 64, 3, 2, 4, 0.0, True, False).to(dev).eval()
+    x = torch.randn(600, 64, generator=torch.Generator().manual_seed(2)).to(dev)
+    nt, ei, et = g.node_type.to(dev), g.edge_index.to(dev), g.edge_type.to(dev)
+    counts = torch.bincount(g.node_type, minlength=3).tolist()
+    pairs = sorted({(int(g.node_type[s]), int(r)) for s, r in zip(g.edge_index[0].tolist(), g.edge_type.tolist())})
+    outs, grads = [], []
+    for meta in (None, {"type_count": counts + [0], "sorted": True, "pairs": pairs}):
+        P.clear_plan_cache()
+        pl = P.get_plan(nt, ei, et, None, 3, 2, host_meta=meta)
+        assert (pl.tile_counts_dev is not None) == (meta is not None)
+        if meta is not None:
+            assert pl.n_hubs >= 1 and pl.n_split >= 3
+        with torch.no_grad():
+            outs.append(m(x, nt, ei, et).clone())
+        xg = x.clone().requires_grad_(True)
+        m(xg, nt, ei, et).square().sum().backward()
+        grads.append(xg.grad.clone())
+        m.zero_grad()
+    P.clear_plan_cache()
+    _close(outs[1], outs[0], "sync-free vs synchronous plan (hubs)", atol=1e-6)
+    _close(grads[1], grads[0], "sync-free vs synchronous plan (hubs), d x", atol=1e-5)
