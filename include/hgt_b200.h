@@ -247,9 +247,11 @@ int hgt_act_split(const float* in, int64_t ld, int64_t rows, int32_t K, int32_t 
 /* Backward of hgt_update_epilogue (conv.py:129-133).  dout [N,d] in ORIGINAL node order (perm as in the forward);
  * o / x [N,d] rank order (the forward's inputs); norm_w [T,d] or NULL.  Outputs: d_o, d_x [N,d] rank order (rows of
  * out-of-range type get zeros), d_skip [T], d_norm_w / d_norm_b [T,d] (zero-initialised by this call).
- * skip == NULL: residual mode (y = o + x), d_skip is not touched. */
+ * skip == NULL: residual mode (y = o + x), d_skip is not touched.  type_active as in the forward: rows past
+ * type_active[t] get zero gradients and their (never computed) `o` rows are not read. */
 int hgt_update_backward(const float* dout, const float* o, const float* x, const int32_t* type_row0, int32_t num_types,
-                        const float* skip, const float* norm_w, const int32_t* perm, int64_t n_nodes, int32_t d,
+                        const float* skip, const float* norm_w, const int32_t* perm, const int32_t* type_active,
+                        int64_t n_nodes, int32_t d,
                         float* d_o, float* d_x, float* d_skip, float* d_norm_w, float* d_norm_b, void* stream);
 
 /* Backward of hgt_fold_weights for the K'/V' blocks: from d W_cat / d b_cat to the gradients of k_linears / v_linears

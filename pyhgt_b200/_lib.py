@@ -44,7 +44,7 @@ SIGNATURES = {
     "hgt_typed_linear_bwd": [_p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p,
                              _i32, _p, _sz, _p],
     "hgt_act_split": [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p],
-    "hgt_update_backward": [_p, _p, _p, _p, _i32, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p],
+    "hgt_update_backward": [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p],
     "hgt_fold_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p,
                           _p, _p, _p, _p, _p],
     "hgt_conv_workspace_bytes": [_p, _c.POINTER(_sz)],

@@ -207,19 +207,21 @@ class _UpdateEpilogue(torch.autograd.Function):
     type_row0[T] are written as zeros), perm: rank-order row -> output row, or None."""
 
     @staticmethod
-    def forward(ctx, o, x, skip, norm_w, norm_b, type_row0, T, perm):
+    def forward(ctx, o, x, skip, norm_w, norm_b, type_row0, T, perm, type_active=None):
         N, d = o.shape
         o, x = o.contiguous(), x.contiguous()
-        out = torch.empty((N, d), dtype=torch.float32, device=o.device)
+        # with type_active (sharded training) the rows past the active prefix of a type have no output: keep them zero
+        out = (torch.zeros if type_active is not None else torch.empty)((N, d), dtype=torch.float32, device=o.device)
         _lib.call("hgt_update_epilogue", o.data_ptr(), x.data_ptr(), type_row0.data_ptr(), T, _lib.ptr(skip),
-                  _lib.ptr(norm_w), _lib.ptr(norm_b), _lib.ptr(perm), None, N, d, out.data_ptr(), None, None, _stream())
+                  _lib.ptr(norm_w), _lib.ptr(norm_b), _lib.ptr(perm), _lib.ptr(type_active), N, d, out.data_ptr(), None,
+                  None, _stream())
         ctx.T, ctx.has_norm, ctx.has_skip = T, norm_w is not None, skip is not None
-        ctx.save_for_backward(o, x, skip, norm_w, type_row0, perm)
+        ctx.save_for_backward(o, x, skip, norm_w, type_row0, perm, type_active)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        o, x, skip, norm_w, type_row0, perm = ctx.saved_tensors
+        o, x, skip, norm_w, type_row0, perm, type_active = ctx.saved_tensors
         T = ctx.T
         N, d = o.shape
         dev = o.device
@@ -229,23 +231,28 @@ class _UpdateEpilogue(torch.autograd.Function):
         d_nw = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
         d_nb = torch.empty((T, d), dtype=torch.float32, device=dev) if ctx.has_norm else None
         _lib.call("hgt_update_backward", dout.data_ptr(), o.data_ptr(), x.data_ptr(), type_row0.data_ptr(), T,
-                  _lib.ptr(skip), _lib.ptr(norm_w), _lib.ptr(perm), N, d, d_o.data_ptr(), d_x.data_ptr(),
-                  _lib.ptr(d_skip), _lib.ptr(d_nw), _lib.ptr(d_nb), _stream())
-        return d_o, d_x, d_skip, d_nw, d_nb, None, None, None
+                  _lib.ptr(skip), _lib.ptr(norm_w), _lib.ptr(perm), _lib.ptr(type_active), N, d, d_o.data_ptr(),
+                  d_x.data_ptr(), _lib.ptr(d_skip), _lib.ptr(d_nw), _lib.ptr(d_nb), _stream())
+        return d_o, d_x, d_skip, d_nw, d_nb, None, None, None, None
 
 
 def typed_linear(a, w_cat, b_cat, table, width, out_elems, impl=0, act=0, zero_ranges=()):
     return _TypedLinear.apply(a, w_cat, b_cat, table, width, out_elems, impl, act, tuple(zero_ranges))
 
 
-def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
+def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time, active=None):
+    """`active` (sharded training): active[t] = number of leading nodes of type t (rank order) that are destinations on
+    this rank; Q / a_linear / update run for them only, the remaining rows (halo sources) only get K'/V' rows and their
+    output rows stay zero."""
     d_in, d, H, T, R = m.in_dim, m.out_dim, m.n_heads, m.num_types, m.num_relations
     plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if m.use_RTE else None, T, R)
     N, P = plan.n_nodes, plan.n_pairs
     if node_inp.shape[0] != N:
         raise ValueError("node_inp has %d rows but node_type has %d" % (node_inp.shape[0], N))
     x = node_inp if plan.sorted_types else node_inp.index_select(0, plan.perm.long())
-    lt = _plan.layer_tables(plan, d_in, d)
+    if active is not None and not plan.sorted_types:
+        raise ValueError("`active` needs a type-sorted node order")
+    lt = _plan.layer_tables(plan, d_in, d, active)
 
     # 1. relation matrices folded into the typed K/V weights; typed projections -> flat [Q | pad | K'V' table | zero row]
     params = ([l.weight for l in m.q_linears] + [l.bias for l in m.q_linears] +
@@ -279,7 +286,7 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time):
     norm_w = torch.stack([n.weight for n in m.norms]) if m.use_norm else None
     norm_b = torch.stack([n.bias for n in m.norms]) if m.use_norm else None
     return _UpdateEpilogue.apply(o, x, m.skip, norm_w, norm_b, plan.type_row0_dev, T,
-                                 None if plan.sorted_types else plan.perm)
+                                 None if plan.sorted_types else plan.perm, lt.type_active_dev)
 
 
 def dense_hgt_forward(m, node_inp, node_type, edge_index, edge_type, edge_time):

@@ -18,7 +18,8 @@ template <int NPL>
 __global__ void __launch_bounds__(UB_WARPS * 32)
 k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const float* __restrict__ x,
              const int32_t* __restrict__ type_row0, int T, const float* __restrict__ skip,
-             const float* __restrict__ norm_w, const int32_t* __restrict__ perm, int64_t n_nodes, int d,
+             const float* __restrict__ norm_w, const int32_t* __restrict__ perm,
+             const int32_t* __restrict__ type_active, int64_t n_nodes, int d,
              float* __restrict__ d_o, float* __restrict__ d_x, float* __restrict__ d_skip, float* __restrict__ d_nw,
              float* __restrict__ d_nb) {
   extern __shared__ float s_red[];                  // [2*d + 1] block-level partial sums (uniform-type blocks)
@@ -81,7 +82,9 @@ k_update_bwd(const float* __restrict__ dout, const float* __restrict__ o, const 
     if (t != cur_t) { flush(cur_t); cur_t = t; }
     float* dorow = d_o + row * d;
     float* dxrow = d_x + row * d;
-    if (t >= T) {                                   // unknown type: the forward wrote zeros (conv.py:120)
+    // unknown type: the forward wrote zeros (conv.py:120); rows past type_active[t] (sharded runs: halo sources) had no
+    // output row at all: neither contributes a gradient, and their `o` rows were never computed
+    if (t >= T || (type_active && row - type_row0[t] >= type_active[t])) {
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int c = lane + 32 * i;
@@ -249,19 +252,21 @@ __global__ void k_fold_bwd_rel(const float* __restrict__ g_w, const float* __res
 
 template <int NPL>
 void launch_update_bwd(const float* dout, const float* o, const float* x, const int32_t* type_row0, int T,
-                       const float* skip, const float* norm_w, const int32_t* perm, int64_t n, int d, float* d_o,
+                       const float* skip, const float* norm_w, const int32_t* perm, const int32_t* type_active,
+                       int64_t n, int d, float* d_o,
                        float* d_x, float* d_skip, float* d_nw, float* d_nb, cudaStream_t st) {
   const int rows_per_block = UB_WARPS * UB_ROWS_PER_WARP;
   const unsigned grid = (unsigned)((n + rows_per_block - 1) / rows_per_block);
   k_update_bwd<NPL><<<grid, UB_WARPS * 32, (2 * d + 1) * sizeof(float), st>>>(dout, o, x, type_row0, T, skip, norm_w, perm,
-                                                                             n, d, d_o, d_x, d_skip, d_nw, d_nb);
+                                                                             type_active, n, d, d_o, d_x, d_skip, d_nw,
+                                                                             d_nb);
 }
 
 }  // namespace
 
 extern "C" int hgt_update_backward(const float* dout, const float* o, const float* x, const int32_t* type_row0,
                                    int32_t num_types, const float* skip, const float* norm_w, const int32_t* perm,
-                                   int64_t n_nodes, int32_t d, float* d_o, float* d_x, float* d_skip, float* d_norm_w,
+                                   const int32_t* type_active, int64_t n_nodes, int32_t d, float* d_o, float* d_x, float* d_skip, float* d_norm_w,
                                    float* d_norm_b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(dout && o && x && type_row0 && d_o && d_x && (d_skip || !skip), "hgt_update_backward: NULL argument");
@@ -274,7 +279,7 @@ extern "C" int hgt_update_backward(const float* dout, const float* o, const floa
   }
   if (n_nodes == 0) return 0;
   const int npl = (d + 31) / 32;
-#define HGT_UB(N) launch_update_bwd<N>(dout, o, x, type_row0, num_types, skip, norm_w, perm, n_nodes, d, d_o, d_x, d_skip, \
+#define HGT_UB(N) launch_update_bwd<N>(dout, o, x, type_row0, num_types, skip, norm_w, perm, type_active, n_nodes, d, d_o, d_x, d_skip, \
                                        d_norm_w, d_norm_b, st)
   if (npl <= 2) HGT_UB(2);
   else if (npl <= 4) HGT_UB(4);

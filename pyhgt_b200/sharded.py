@@ -294,7 +294,15 @@ class ShardedGraph:
         layer's autograd path on the local graph, owned rows out.  Parameter gradients are PARTIAL per rank (each rank
         sees only its destinations): sum them with `allreduce_grads` (or wrap the model in DistributedDataParallel)."""
         x_local = _HaloExchange.apply(x_own, self)
-        out = conv(x_local, self.node_type, self.edge_index, self.edge_type, self.edge_time if conv.use_RTE else None)
+        tm = self.edge_time if conv.use_RTE else None
+        if x_local.is_cuda and hasattr(conv, "q_linears") and type(conv).__name__ == "HGTConv":
+            # only the owned prefix of every type is a destination here: Q / a_linear / update skip the halo rows
+            from .autograd import hgt_conv_autograd
+            conv._check_inputs(x_local, tm)
+            out = hgt_conv_autograd(conv, x_local, self.node_type, self.edge_index, self.edge_type, tm,
+                                    active=self.active_per_type)
+        else:
+            out = conv(x_local, self.node_type, self.edge_index, self.edge_type, tm)
         return out.index_select(0, self.own_rows)
 
     def allreduce_grads(self, module):

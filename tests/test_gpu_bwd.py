@@ -147,7 +147,7 @@ def test_update_backward_matches_fp64():
         od, xd, gd, sd, nwd = o.to(dev), x.to(dev), g.to(dev), skip.to(dev), nw.to(dev)
         pd = perm.to(torch.int32).to(dev)
         _lib.call("hgt_update_backward", gd.data_ptr(), od.data_ptr(), xd.data_ptr(), tr0.data_ptr(), T, sd.data_ptr(),
-                  nwd.data_ptr() if use_norm else None, pd.data_ptr(), N, d, d_o.data_ptr(), d_x.data_ptr(), d_s.data_ptr(),
+                  nwd.data_ptr() if use_norm else None, pd.data_ptr(), None, N, d, d_o.data_ptr(), d_x.data_ptr(), d_s.data_ptr(),
                   d_nw.data_ptr() if use_norm else None, d_nb.data_ptr() if use_norm else None,
                   torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
