@@ -460,6 +460,13 @@ def main_ours(args, rank, local_rank, world):
             stage_lists.setdefault(n, []).append(a.elapsed_time(b))
         stages = {k: _median(v) * (len(v) / args.steps) for k, v in stage_lists.items()}
         HGTConv.event_sink = None
+        stages_all = None
+        if world > 1:                                   # every rank's stage medians: imbalance shows up as halo wait
+            names = sorted(stages)
+            mine = torch.tensor([stages[n] for n in names], device=dev, dtype=torch.float64)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            stages_all = {n: [round(float(r[i]), 3) for r in allr] for i, n in enumerate(names)}
         clocks = sampler.stop() if sampler is not None else None
         value = E / (ms_step * 1e-3)
 
@@ -641,7 +648,7 @@ def main_ours(args, rank, local_rank, world):
                             "median": ms_step, "mean": sum(per_step) / len(per_step), "min": min(per_step),
                             "max": max(per_step), "list": [round(v, 3) for v in per_step]},
                 "roofline": roofline, "roofline_linear": roofline_linear,
-                "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
+                "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()}, "stage_ms_all_ranks": stages_all,
                 "halo_modes_max_abs_diff": halo_diff, "parity_max_abs_diff": parity,
                 "parity": None if parity is None else
                 "%d sampled destination rows (all ranks) vs the single-GPU path on their 1-hop induced subgraph"
