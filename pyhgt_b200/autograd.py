@@ -18,6 +18,7 @@ The inference path (``torch.no_grad``) does not come through here: it uses the f
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -337,7 +338,7 @@ def dense_hgt_forward(m, node_inp, node_type, edge_index, edge_type, edge_time):
     if tabs is None:
         one = lambda w_: _plan._pack_groups([(0, n_known, 0, 1, 0, 1)], [(0, w_)], dev)            # noqa: E731
         tabs = plan._layer_tables[key] = (one(2 * d), one(d),
-                                          torch.tensor([0, n_known, N], dtype=torch.int32).to(dev))
+                                          _plan._to_dev_async(np.asarray([0, n_known, N], dtype=np.int32), dev))
     hmid = typed_linear(y, m.mid_linear.weight, m.mid_linear.bias, tabs[0], 2 * d, N * 2 * d, m.linear_impl, 0,
                         ((n_known * 2 * d, N * 2 * d),)).view(N, 2 * d)
     z = typed_linear(hmid, m.out_linear.weight, m.out_linear.bias, tabs[1], d, N * d, m.linear_impl, 1,

@@ -122,12 +122,32 @@ def _as_i64(t, name, device):
     return t.contiguous()
 
 
+_PIN_KEEP = None     # a list while a CUDA graph is being captured (graphed.py): captured H2D copies re-read their pinned
+                     # sources at every replay, so those must outlive the capture
+
+
 def _to_dev_async(arr, dev):
     """Small host table -> device through pinned staging, without synchronising the stream."""
     t = torch.from_numpy(arr)
     if dev.type == "cuda":
-        return t.pin_memory().to(dev, non_blocking=True)
+        pinned = t.pin_memory()
+        if _PIN_KEEP is not None:
+            _PIN_KEEP.append(pinned)
+        return pinned.to(dev, non_blocking=True)
     return t.to(dev)
+
+
+def rebuild_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, host_meta):
+    """Build the plan of these tensors NOW (dropping a cached one) and cache it: the layers called next find it.  Used by
+    graphed.py so that the plan build itself lands inside the captured CUDA graph."""
+    tensors = (node_type, edge_index, edge_type, edge_time)
+    for i in range(len(_CACHE) - 1, -1, -1):
+        refs = _CACHE[i][0]
+        if all((r is None and t is None) or (r is not None and r() is t) for r, t in zip(refs, tensors)):
+            _CACHE.pop(i)
+    plan = build_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, host_meta)
+    _cache_store(tensors, (num_types, num_relations), plan)
+    return plan
 
 
 def get_plan(node_type, edge_index, edge_type, edge_time, num_types, num_relations, use_cache=True, host_meta=None):

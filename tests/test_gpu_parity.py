@@ -731,3 +731,37 @@ def test_sync_free_plan_with_hubs_matches_synchronous_plan():
     P.clear_plan_cache()
     _close(outs[1], outs[0], "sync-free vs synchronous plan (hubs)", atol=1e-6)
     _close(grads[1], grads[0], "sync-free vs synchronous plan (hubs), d x", atol=1e-5)
+
+
+def test_cuda_graph_replay_of_plan_and_layers_matches_eager():
+    """graphed.GraphedForward: plan build + a 2-layer GNN captured once for a padded signature, replayed for batches of
+    different sizes; every batch equals the eager result on the unpadded batch."""
+    from pyhgt_b200.model import GNN
+    from pyhgt_b200 import graphed
+    dev = _dev()
+    T, R, F_in, n_hid = 3, 4, 48, 64
+    torch.manual_seed(3)
+    m = GNN(F_in, n_hid, T, R, 4, 2, 0.2, "hgt", True, False, True).to(dev).eval()
+    batches = [synth.make_random(n, e, T, R, seed=s, sorted_types=True, self_loops=20)
+               for n, e, s in ((400, 3000, 1), (310, 2200, 2), (455, 3400, 3))]
+    counts = [max(int((b.node_type == t).sum()) for b in batches) + 5 for t in range(T)]
+    pairs = {(int(b.node_type[s_]), int(r_)) for b in batches for s_, r_ in zip(b.edge_index[0].tolist(), b.edge_type.tolist())}
+    sig = graphed.GraphSignature(counts, 3600, pairs, R, F_in, use_time=True)
+    g = graphed.GraphedForward(lambda x, nt, tm, ei, et: m(x, nt, tm, ei, et), sig, dev)
+    old_keep = __import__("pyhgt_b200").HGTConv.keep_att
+    __import__("pyhgt_b200").HGTConv.keep_att = False
+    try:
+        for rep in range(2):
+            for b in batches:
+                x = torch.randn(b.num_nodes, F_in, generator=torch.Generator().manual_seed(7 + b.num_nodes))
+                out = g(x, b.node_type, b.edge_time, b.edge_index, b.edge_type)
+                with torch.no_grad():
+                    ref = m(x.to(dev), b.node_type.to(dev), b.edge_time.to(dev), b.edge_index.to(dev), b.edge_type.to(dev))
+                torch.cuda.synchronize()
+                _close(out, ref, "graph replay vs eager (N=%d, pass %d)" % (b.num_nodes, rep), atol=1e-5)
+    finally:
+        __import__("pyhgt_b200").HGTConv.keep_att = old_keep
+    # a batch that does not fit is refused, not silently truncated
+    big = synth.make_random(2000, 3000, T, R, seed=9, sorted_types=True)
+    with pytest.raises(ValueError):
+        g(torch.randn(2000, F_in), big.node_type, big.edge_time, big.edge_index, big.edge_type)
