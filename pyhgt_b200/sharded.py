@@ -17,11 +17,13 @@ import torch.distributed as dist
 
 
 def partition_owner(node_type, edge_index, num_types, world):
-    """owner[n] in [0, world): contiguous cost-balanced blocks inside every node type (deterministic, CPU)."""
+    """owner[n] in [0, world): contiguous cost-balanced blocks inside every node type (deterministic; runs on the device
+    of its inputs)."""
     n = node_type.numel()
+    wdev = node_type.device
     deg = torch.bincount(edge_index[1], minlength=n)
     cost = 2 * deg + 1
-    owner = torch.zeros(n, dtype=torch.int64)
+    owner = torch.zeros(n, dtype=torch.int64, device=wdev)
     for t in range(num_types):
         ids = (node_type == t).nonzero(as_tuple=True)[0]           # ascending ids = stable type order
         if ids.numel() == 0:
@@ -34,7 +36,7 @@ def partition_owner(node_type, edge_index, num_types, world):
     other = (node_type < 0) | (node_type >= num_types)
     if other.any():
         ids = other.nonzero(as_tuple=True)[0]
-        owner[ids] = torch.arange(ids.numel()) * world // max(ids.numel(), 1)
+        owner[ids] = torch.arange(ids.numel(), device=wdev) * world // max(ids.numel(), 1)
     return owner
 
 
@@ -100,19 +102,24 @@ class ShardedGraph:
     def build(node_type, edge_index, edge_type, edge_time, num_types, num_relations, rank, world, device,
               group=None, halo_mode=None):
         import os
-        node_type, edge_index, edge_type = node_type.cpu(), edge_index.cpu(), edge_type.cpu()
-        edge_time = None if edge_time is None else edge_time.cpu()
+        # the O(N + E) passes below are plain tensor ops: run them on the target GPU when there is one (C2: 3.5 s on the
+        # host cores vs a fraction of a second on the device); the id lists callers index host arrays with come back to
+        # the CPU at the end
+        wdev = torch.device(device) if torch.device(device).type == "cuda" else torch.device("cpu")
+        node_type, edge_index, edge_type = node_type.to(wdev), edge_index.to(wdev), edge_type.to(wdev)
+        edge_time = None if edge_time is None else edge_time.to(wdev)
         n = node_type.numel()
+        i64 = dict(dtype=torch.int64, device=wdev)
         owner = partition_owner(node_type, edge_index, num_types, world)
         tkey = torch.where((node_type >= 0) & (node_type < num_types), node_type, torch.full_like(node_type, num_types))
         # position of every node inside its owner's (type-sorted) owned list — identical on every rank
-        owned_pos = torch.empty(n, dtype=torch.int64)
+        owned_pos = torch.empty(n, **i64)
         max_owned = 0
         owned = None
         for r in range(world):
             mine_r = (owner == r).nonzero(as_tuple=True)[0]
             owned_r = mine_r[torch.argsort(tkey[mine_r], stable=True)]
-            owned_pos[owned_r] = torch.arange(owned_r.numel())
+            owned_pos[owned_r] = torch.arange(owned_r.numel(), device=wdev)
             max_owned = max(max_owned, int(owned_r.numel()))
             if r == rank:
                 owned = owned_r
@@ -128,9 +135,9 @@ class ShardedGraph:
         # <source type, relation> pair really needs form a few contiguous runs: K'/V' are projected for those runs only
         # (kv_runs) instead of for every local node of the type.
         cat_ids = torch.cat([owned, halo])                                   # order of concat([x_own, recv])
-        is_halo = torch.cat([torch.zeros(n_owned, dtype=torch.int64), torch.ones(n_halo, dtype=torch.int64)])
+        is_halo = torch.cat([torch.zeros(n_owned, **i64), torch.ones(n_halo, **i64)])
         rel_sel = edge_type[e_sel]
-        rel_mask = torch.zeros(n, dtype=torch.int64)
+        rel_mask = torch.zeros(n, **i64)
         compact = num_relations <= 16
         if compact:
             for r in range(num_relations):
@@ -156,12 +163,13 @@ class ShardedGraph:
                     has = ((mt >> r) & 1).to(torch.int8)
                     if int(has.sum()) == 0:
                         continue
-                    edge_ = torch.diff(torch.cat([torch.zeros(1, dtype=torch.int8), has, torch.zeros(1, dtype=torch.int8)]))
+                    z8 = torch.zeros(1, dtype=torch.int8, device=wdev)
+                    edge_ = torch.diff(torch.cat([z8, has, z8]))
                     starts = (edge_ == 1).nonzero(as_tuple=True)[0].tolist()
                     ends = (edge_ == -1).nonzero(as_tuple=True)[0].tolist()
                     kv_runs[(t, r)] = tuple(zip(starts, ends))
-        local_of = torch.full((n,), -1, dtype=torch.int64)
-        local_of[local_global] = torch.arange(local_global.numel())
+        local_of = torch.full((n,), -1, **i64)
+        local_of[local_global] = torch.arange(local_global.numel(), device=wdev)
         ei_local = torch.stack([local_of[src], local_of[dst]])
         recv_splits = torch.bincount(owner[halo], minlength=world).tolist()
         send_lists = []
@@ -169,19 +177,19 @@ class ShardedGraph:
         src_owner_all = owner[edge_index[0]]
         for p in range(world):
             if p == rank:
-                send_lists.append(torch.zeros(0, dtype=torch.int64))
+                send_lists.append(torch.zeros(0, **i64))
                 continue
             need = (dst_owner_all == p) & (src_owner_all == rank)
             ids = torch.unique(edge_index[0, need.nonzero(as_tuple=True)[0]])   # ascending = the peer's arrival order
             send_lists.append(owned_pos[ids])
         send_splits = [int(x.numel()) for x in send_lists]
-        send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, dtype=torch.int64)
+        send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, **i64)
         active = torch.bincount(tkey[owned], minlength=num_types + 1).tolist()
         # "auto" (default): fused peer-memory pull on CUDA, NCCL all_to_all if symmetric memory is unavailable
         mode = halo_mode or os.environ.get("HGT_HALO", "auto")
         return ShardedGraph(rank=rank, world=world, device=device, n_owned=n_owned, n_halo=n_halo,
-                            n_local_edges=int(e_sel.numel()), owned_global=owned, halo_global=halo,
-                            local_global=local_global, node_type=node_type[local_global].to(device),
+                            n_local_edges=int(e_sel.numel()), owned_global=owned.cpu(), halo_global=halo.cpu(),
+                            local_global=local_global.cpu(), node_type=node_type[local_global].to(device),
                             edge_index=ei_local.to(device), edge_type=edge_type[e_sel].to(device),
                             edge_time=None if edge_time is None else edge_time[e_sel].to(device),
                             send_idx=send_idx.to(device), send_splits=send_splits, recv_splits=recv_splits,
