@@ -101,6 +101,13 @@ k_update_epilogue_vec(const float* __restrict__ o, const float* __restrict__ x, 
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   const int nvec = d >> 2;
+  if (type_active) {
+    // sharded runs: most local rows may be halo sources without an output row — leave before touching their data
+    int t0 = 0;
+    while (t0 < T && row >= type_row0[t0 + 1]) ++t0;
+    if (t0 < T && row - type_row0[t0] >= type_active[t0]) return;
+    if (perm && perm[row] < 0) return;
+  }
   // issue the row loads first; the (short, warp-uniform) type search overlaps with them
   float4 ov[NV], xv[NV];
   const float4* op = reinterpret_cast<const float4*>(o + row * d);
