@@ -190,7 +190,9 @@ int hgt_typed_linear_presplit(const void* a_hi, const void* a_lo, const float* W
  *  variant: 0 = auto, 1 = direct register gather (LDG), 2 = bulk-async-copy shared-memory ring (TMA)
  *  d_tile_counts: NULL, or the device counts {n_tiles, n_split, n_hubs} hgt_plan_tiles wrote in its sync-free mode; then
  *           n_tiles / n_split_tiles / n_hubs are the UPPER BOUNDS the arrays were sized with and the kernels read the
- *           true counts from the device (no host read-back between plan build and layer). */
+ *           true counts from the device (no host read-back between plan build and layer).
+ *  type_row0 [T+2] / type_active [T]: NULL, or (sharded runs) the same tables hgt_update_epilogue takes: destinations
+ *           past the active prefix of their type are halo sources — they have no in-edges and no output row is written. */
 int hgt_edge_workspace_bytes(int32_t n_split_tiles, int32_t d, int32_t n_heads, size_t* out_bytes);
 int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      const int32_t* row_ptr, const int32_t* kv_row, const int32_t* rte_row,
@@ -199,7 +201,7 @@ int hgt_edge_forward(const float* q, const float* kv, const float* kvr,
                      int64_t n_nodes, int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu,
                      float* agg_out, float* att_out, float* stats_out, void* g_hi, void* g_lo,
                      void* workspace, size_t workspace_bytes, int32_t variant, const int32_t* d_tile_counts,
-                     void* stream);
+                     const int32_t* type_row0, int32_t num_types, const int32_t* type_active, void* stream);
 
 /* Backward of hgt_edge_forward (training; the reference differentiates the same ops with autograd,
  * OAG/train_paper_field.py:249).  Inputs: the forward's q / kv / kvr tables, its un-activated output

@@ -35,7 +35,7 @@ SIGNATURES = {
     "hgt_typed_linear": [_p, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _sz, _p],
     "hgt_edge_workspace_bytes": [_i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_edge_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p,
-                         _p, _p, _p, _p, _sz, _i32, _p, _p],
+                         _p, _p, _p, _p, _sz, _i32, _p, _p, _i32, _p, _p],
     "hgt_typed_linear_presplit_workspace_bytes": [_p, _i32, _i32, _i32, _c.POINTER(_sz)],
     "hgt_typed_linear_presplit": [_p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p],
     "hgt_edge_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _sz,

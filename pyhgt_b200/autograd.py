@@ -127,7 +127,8 @@ class _EdgeAttention(torch.autograd.Function):
                   plan.kv_row.data_ptr(), None if kvr is None else plan.rte_row.data_ptr(), plan.csr_eid.data_ptr(),
                   plan.tiles.data_ptr(), plan.n_tiles, plan.n_split, plan.hubs.data_ptr(), plan.n_hubs, N, plan.n_edges, d,
                   n_heads, 0, agg.data_ptr(), _lib.ptr(att), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
-                  variant, _lib.ptr(plan.tile_counts_dev), _stream())
+                  variant, _lib.ptr(plan.tile_counts_dev), plan.type_row0_dev.data_ptr(), plan.num_types,
+                  _lib.ptr(lt.type_active_dev), _stream())
         ctx.plan, ctx.lt, ctx.d, ctx.n_heads, ctx.has_kvr = plan, lt, d, n_heads, kvr is not None
         ctx.save_for_backward(proj, kvr, agg, stats)
         if att is not None:

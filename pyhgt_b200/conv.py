@@ -408,7 +408,8 @@ class HGTConv(nn.Module):
                       plan.csr_eid.data_ptr(), plan.tiles.data_ptr(), plan.n_tiles, plan.n_split,
                       plan.hubs.data_ptr(), plan.n_hubs, N, E, d, H, 1 if (gelu_before_a and not save) else 0,
                       _lib.ptr(g_act), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(g_hi), _lib.ptr(g_lo), ws.data_ptr(),
-                      ws.numel(), self.edge_variant, _lib.ptr(plan.tile_counts_dev), st)
+                      ws.numel(), self.edge_variant, _lib.ptr(plan.tile_counts_dev), plan.type_row0_dev.data_ptr(), T,
+                      _lib.ptr(lt.type_active_dev), st)
 
         # 4. typed output linear (conv.py:125 / conv.py:261)
         agg = None

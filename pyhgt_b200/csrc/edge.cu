@@ -36,6 +36,9 @@ struct EdgeParams {
   const int32_t* tiles;
   int32_t n_tiles;           // exact count, or an upper bound when d_counts is given
   const int32_t* d_counts;   // optional device {n_tiles, n_split, n_hubs} written by hgt_plan_tiles (sync-free plans)
+  const int32_t* type_row0;  // optional (with type_active): [T+2] row prefix per type
+  const int32_t* type_active;// optional [T]: rows past type_active[t] inside type t are halo sources without an output
+  int32_t T;
   int32_t d, H, DK, LPH, lph_shift;
   int32_t apply_gelu;
   float* agg_out;            // nullptr when only the split bf16 copy is wanted
@@ -47,6 +50,13 @@ struct EdgeParams {
   int32_t* tile_counter;
   int32_t stages;            // TMA variant
 };
+
+// sharded runs: destination `dst` lies past the active (owned) prefix of its node type
+__device__ __forceinline__ bool dst_inactive(const EdgeParams& p, int dst) {
+  int t = 0;
+  while (t < p.T && dst >= p.type_row0[t + 1]) ++t;
+  return t < p.T && dst - p.type_row0[t] >= p.type_active[t];
+}
 
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using type = float; };
@@ -215,6 +225,7 @@ k_edge_fwd_ldg(EdgeParams p) {
     int seg_begin = tl.z;
     for (int dst = d_begin; dst < d_end; ++dst) {
       const int seg_end = split ? tl.w : p.row_ptr[dst + 1];
+      if (p.type_active && seg_end == seg_begin && dst_inactive(p, dst)) continue;   // halo row: no output wanted
       LaneState<VEC, NCH> st;
       st.reset();
       if (seg_end > seg_begin) {
@@ -421,6 +432,7 @@ k_edge_fwd_tma(EdgeParams p) {
     int seg_begin = e0;
     for (int dst = d_begin; dst < d_end; ++dst) {
       const int seg_end = split ? e1 : p.row_ptr[dst + 1];
+      if (p.type_active && seg_end == seg_begin && dst_inactive(p, dst)) continue;   // halo row: no output wanted
       LaneState<VEC, NCH> st;
       st.reset();
       if (seg_end > seg_begin) {
@@ -602,6 +614,7 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
                                 int64_t n_edges, int32_t d, int32_t n_heads, int32_t apply_gelu, float* agg_out,
                                 float* att_out, float* stats_out, void* g_hi, void* g_lo, void* workspace,
                                 size_t workspace_bytes, int32_t variant, const int32_t* d_tile_counts,
+                                const int32_t* type_row0, int32_t num_types, const int32_t* type_active,
                                 void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   (void)n_edges;
@@ -618,7 +631,8 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
 
   EdgeParams p;
   p.q = q; p.kv = kv; p.kvr = kvr; p.row_ptr = row_ptr; p.kv_row = kv_row; p.rte_row = rte_row;
-  p.csr_eid = csr_eid; p.tiles = tiles; p.n_tiles = n_tiles; p.d_counts = d_tile_counts; p.d = d; p.H = n_heads; p.DK = d / n_heads;
+  p.csr_eid = csr_eid; p.tiles = tiles; p.n_tiles = n_tiles; p.d_counts = d_tile_counts; p.d = d;
+  p.type_row0 = type_row0; p.type_active = (type_row0 && num_types > 0) ? type_active : nullptr; p.T = num_types; p.H = n_heads; p.DK = d / n_heads;
   int hp = 1, shift = 5;
   while (hp < n_heads) hp <<= 1;
   p.LPH = 32 / hp;

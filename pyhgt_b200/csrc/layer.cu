@@ -138,7 +138,8 @@ extern "C" int hgt_conv_forward(const hgt_conv_args* a, void* workspace, size_t 
   if ((rc = hgt_edge_forward(L.proj + a->q_off, L.proj + a->kv_off, L.kvr, a->row_ptr, a->kv_row,
                              a->use_rte ? a->rte_row : nullptr, a->csr_eid, a->tiles, a->n_tiles, a->n_split, a->hubs,
                              a->n_hubs, N, a->n_edges, d, a->n_heads, 1, L.g_act, a->att, nullptr, L.g_hi, L.g_lo,
-                             L.ws_edge, L.ws_edge_bytes, a->edge_variant, a->d_tile_counts, stream)))
+                             L.ws_edge, L.ws_edge_bytes, a->edge_variant, a->d_tile_counts, a->type_row0, T,
+                             a->type_active, stream)))
     return rc;
   if ((rc = hgt_concat_linears(a->wa, a->ba, T, d, d, L.wa_cat, L.ba_cat, stream))) return rc;
   if (L.fuse_split)
