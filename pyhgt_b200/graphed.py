@@ -34,6 +34,11 @@ class GraphSignature:
         self.use_time = bool(use_time)
         self.n_nodes = sum(self.type_counts) + 1            # + the trailing out-of-range-type node
         self.row0 = np.concatenate([[0], np.cumsum(self.type_counts)]).astype(np.int64)
+        self.pair_mask = np.zeros(self.num_types * self.num_relations, dtype=bool)
+        for s_, r_ in self.pairs:
+            if 0 <= s_ < self.num_types and 0 <= r_ < self.num_relations:
+                self.pair_mask[s_ * self.num_relations + r_] = True
+        self.node_type = np.repeat(np.arange(self.num_types + 1, dtype=np.int64), self.type_counts + [1])   # static
 
     def fits(self, counts, n_edges, pairs):
         return (len(counts) == self.num_types and all(c <= C for c, C in zip(counts, self.type_counts))
@@ -43,39 +48,51 @@ class GraphSignature:
         return {"type_count": self.type_counts + [1], "sorted": True, "pairs": self.pairs}
 
 
-def pad_batch(sig, node_feature, node_type, edge_time, edge_index, edge_type):
+def pad_batch(sig, node_feature, node_type, edge_time, edge_index, edge_type, out=None):
     """Host tensors of one batch (type-contiguous node order) -> padded numpy arrays of the signature's shape and the
-    new index of every real node.  Raises if the batch does not fit."""
+    new index of every real node.  `out` = (x, edge_time, edge_index, edge_type) numpy views to fill in place (pinned
+    staging).  Raises if the batch does not fit."""
     nt = node_type.numpy()
     if nt.size and np.any(nt[1:] < nt[:-1]):
         raise ValueError("pad_batch needs type-contiguous nodes (what to_torch emits)")
     T = sig.num_types
-    counts = np.bincount(nt, minlength=T)[:T] if nt.size else np.zeros(T, dtype=np.int64)
-    if nt.size and (nt.min() < 0 or nt.max() >= T):
+    if nt.size and (nt[0] < 0 or nt[-1] >= T):
         raise ValueError("pad_batch: node types must lie in [0, %d)" % T)
+    counts = np.bincount(nt, minlength=T)[:T] if nt.size else np.zeros(T, dtype=np.int64)
     src, dst = edge_index[0].numpy(), edge_index[1].numpy()
     et = edge_type.numpy()
     E = et.size
-    pairs = set(zip(nt[src].tolist(), et.tolist())) if E else set()
-    if not sig.fits(counts.tolist(), E, pairs):
+    ok = len(counts) == T and bool(np.all(counts <= np.asarray(sig.type_counts))) and E <= sig.n_edges
+    if ok and E:
+        if et.min() < 0 or et.max() >= sig.num_relations:
+            ok = False
+        else:
+            present = np.bincount(nt[src] * sig.num_relations + et, minlength=T * sig.num_relations) > 0
+            ok = not bool(np.any(present & ~sig.pair_mask))
+    if not ok:
         raise ValueError("batch (type counts %s, %d edges) does not fit the signature (%s, %d edges) or has new "
                          "<type, relation> pairs" % (counts.tolist(), E, sig.type_counts, sig.n_edges))
     old0 = np.concatenate([[0], np.cumsum(counts)])
     shift = sig.row0[:T] - old0[:T]
     new_id = np.arange(nt.size, dtype=np.int64) + shift[nt] if nt.size else np.zeros(0, dtype=np.int64)
-    x = np.zeros((sig.n_nodes, sig.feat_dim), dtype=np.float32)
+    if out is None:
+        out = (np.empty((sig.n_nodes, sig.feat_dim), dtype=np.float32), np.empty(sig.n_edges, dtype=np.int64),
+               np.empty((2, sig.n_edges), dtype=np.int64), np.empty(sig.n_edges, dtype=np.int64))
+    x, etm, ei, ety = out
+    x.fill(0.0)
     x[new_id] = node_feature.numpy()
-    ntype = np.repeat(np.arange(T + 1, dtype=np.int64), sig.type_counts + [1])
     pad_node = sig.n_nodes - 1
-    ei = np.full((2, sig.n_edges), pad_node, dtype=np.int64)
     ei[0, :E] = new_id[src]
     ei[1, :E] = new_id[dst]
-    ety = np.zeros(sig.n_edges, dtype=np.int64)
+    ei[:, E:] = pad_node
     ety[:E] = et
-    etm = np.full(sig.n_edges, 120, dtype=np.int64)
+    ety[E:] = 0
+    etm[E:] = 120
     if edge_time is not None:
         etm[:E] = edge_time.numpy()
-    return x, ntype, etm, ei, ety, new_id
+    else:
+        etm[:E] = 120
+    return x, sig.node_type, etm, ei, ety, new_id
 
 
 class GraphedForward:
@@ -104,6 +121,7 @@ class GraphedForward:
         self.out = None
         self.plan = None
         self._staged = None
+        self._nt_done = False
         self._pins = []
         self.stream = torch.cuda.Stream(device=dev)
 
@@ -114,21 +132,28 @@ class GraphedForward:
         with torch.no_grad():
             return self.fn(self.x, self.nt, self.tm, self.ei, self.et)
 
-    def _stage(self, arrays):
+    def _stage(self, batch):
+        """Pad the batch straight into the pinned staging buffers and enqueue the copies (node_type is static)."""
         if self._staged is not None:
             self._staged.synchronize()                       # the previous batch's copies have left the staging buffers
-        for h, a, dst in zip(self.h, arrays, (self.x, self.nt, self.tm, self.ei, self.et)):
-            h.copy_(torch.from_numpy(a))
+        hx, hnt, htm, hei, het = self.h
+        out = (hx.numpy(), htm.numpy(), hei.numpy(), het.numpy())
+        new_id = pad_batch(self.sig, *batch, out=out)[5]
+        if not self._nt_done:
+            hnt.copy_(torch.from_numpy(self.sig.node_type))
+            self.nt.copy_(hnt, non_blocking=True)
+            self._nt_done = True
+        for h, dst in ((hx, self.x), (htm, self.tm), (hei, self.ei), (het, self.et)):
             dst.copy_(h, non_blocking=True)
         self._staged = torch.cuda.Event()
         self._staged.record(self.stream)
+        return new_id
 
     def __call__(self, node_feature, node_type, edge_time, edge_index, edge_type):
-        x, ntype, etm, ei, ety, new_id = pad_batch(self.sig, node_feature, node_type, edge_time, edge_index, edge_type)
         cur = torch.cuda.current_stream(self.dev)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            self._stage((x, ntype, etm, ei, ety))
+            new_id = self._stage((node_feature, node_type, edge_time, edge_index, edge_type))
             if self.graph is None:
                 for _ in range(2):                          # eager warm-up: pointer tables, pinned-block cache
                     self._run()

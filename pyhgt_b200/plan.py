@@ -87,7 +87,9 @@ def _cache_lookup(tensors, extra):
         if ex != extra:
             continue
         ok = True
-        for r, v, t in zip(refs, versions, tensors):
+        for i, (r, v, t) in enumerate(zip(refs, versions, tensors)):
+            if i == 3 and t is None and r is not None and r() is not None:
+                continue          # a plan built WITH edge_time also serves a layer that does not use it (use_RTE=False)
             if (r is None) != (t is None):
                 ok = False
                 break

@@ -56,6 +56,15 @@ for name, g, d, H in (("c1", synth.make_c1(), 64, 4), ("c1-sorted", synth.make_r
         for _ in range(50):
             gf(xh, g.node_type, g.edge_time, g.edge_index, g.edge_type)
         torch.cuda.synchronize()
-        print("%s: CUDA-graph replay incl. host padding + H2D of the batch: %.3f ms per call" % (name, (time.perf_counter() - t0) / 50 * 1e3))
+        per_call = (time.perf_counter() - t0) / 50 * 1e3
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(gf.stream):
+            ev0.record()
+            for _ in range(20):
+                gf.graph.replay()
+            ev1.record()
+        torch.cuda.synchronize()
+        print("%s: CUDA-graph replay incl. host padding + H2D of the batch: %.3f ms per call; device time of one replay "
+              "(plan build + layer): %.3f ms" % (name, per_call, ev0.elapsed_time(ev1) / 20))
     print("%s: N=%d E=%d d=%d  forward %.3f ms (plan cached)  %.3f ms (plan rebuilt)  -> %.1f / %.1f M edges/s"
           % (name, g.num_nodes, g.num_edges, d, warm, cold, g.num_edges / warm / 1e3, g.num_edges / cold / 1e3))

@@ -677,7 +677,7 @@ def test_sampled_subgraph_batch_runs_without_host_sync():
         ref_sync = m(nf, nt, fx["edge_index"].to(dev), et)                 # synchronous plan (different tensor object)
         out0 = m(nf, nt, ei, et, etime)                                   # warm-up of the sync-free path
     torch.cuda.synchronize()
-    pl = P.get_plan(nt, ei, et, None, T, R)
+    pl = P.get_plan(nt, ei, et, None, T, R)              # the layer asks without edge_time (no RTE): served by the prebuilt plan
     assert pl.tile_counts_dev is not None                                 # the prebuilt plan is the sync-free one
     pl.check()
     P.clear_plan_cache()
