@@ -164,9 +164,84 @@ def to_torch_case(name, seed):
     print("%-28s N=%d E=%d  %.0f KB" % (name, ref[1].numel(), ref[4].numel(), os.path.getsize(path) / 1024))
 
 
+def sampler_graph(data, seed, n_paper=300, n_author=200, n_venue=8, n_field=30, e_ap=1200, e_pp=900, e_pf=700):
+    """A small OAG-like reference Graph built through the reference's own add_edge (rev_ relations included)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    g = data.Graph()
+    years = rng.randint(2000, 2020, size=n_paper)
+
+    def paper(i):
+        return {"type": "paper", "id": "p%d" % i}
+    for i in range(n_paper):
+        g.add_edge(paper(i), {"type": "venue", "id": "v%d" % rng.randint(n_venue)}, time=int(years[i]),
+                   relation_type="PV_Journal")
+    for _ in range(e_ap):
+        p = rng.randint(n_paper)
+        g.add_edge({"type": "author", "id": "a%d" % rng.randint(n_author)}, paper(p), time=int(years[p]),
+                   relation_type="AP_write")
+    for _ in range(e_pp):
+        p, q = rng.randint(n_paper), rng.randint(n_paper)
+        g.add_edge(paper(p), paper(q), time=int(years[q]), relation_type="PP_cite")
+    for _ in range(e_pf):
+        p = rng.randint(n_paper)
+        g.add_edge(paper(p), {"type": "field", "id": "f%d" % rng.randint(n_field)},
+                   time=None if rng.rand() < 0.3 else int(years[p]), relation_type="PF_in_L2")
+    for t in ("paper", "author", "venue", "field"):
+        g.node_feature[t] = []
+    return g, years
+
+
+def sampler_extractor(layer_data, graph):
+    """Stand-in for feature_OAG (data.py:55-84; needs pandas frames and removed numpy aliases): ids and times as the
+    feature, same dict / ordering conventions."""
+    import numpy as np
+    feature, times, indxs = {}, {}, {}
+    for _type in layer_data:
+        if len(layer_data[_type]) == 0:
+            continue
+        idxs = np.array(list(layer_data[_type].keys()))
+        tims = np.array(list(layer_data[_type].values()))[:, 1]
+        feature[_type] = np.stack([idxs, tims], 1).astype(np.float32)
+        times[_type] = tims
+        indxs[_type] = idxs
+    return feature, times, indxs, []
+
+
+def sampler_case(name, seed):
+    """sample_subgraph (data.py:87-210) run by the UNMODIFIED reference with a seeded numpy RNG, then the reference's
+    to_torch on the result.  The fixture stores the graph's edge_list as plain nested dicts (insertion orders kept)."""
+    import numpy as np
+    data = pyg_shim.load_reference_data()
+    g, years = sampler_graph(data, seed)
+    time_range = {int(y): True for y in range(2000, 2016)}
+    pids = np.random.RandomState(100 + seed).choice(300, 24, replace=False)
+    inp = {"paper": np.array([[int(p), int(years[p])] for p in pids])}
+    cases = []
+    for depth, number in ((2, 8), (4, 16)):
+        np.random.seed(7 + seed)
+        feature, times, edge_list, indxs, _ = data.sample_subgraph(g, time_range, depth, number, inp, sampler_extractor)
+        rng_after = np.random.get_state()[1].copy()
+        tt = data.to_torch(feature, times, edge_list, g)
+        cases.append({"depth": depth, "number": number, "np_seed": 7 + seed,
+                      "feature": feature, "times": times, "indxs": indxs,
+                      "edge_list": [(t, s, r, np.asarray(edge_list[t][s][r], dtype=np.int64).reshape(-1, 2))
+                                    for t in edge_list for s in edge_list[t] for r in edge_list[t][s]],
+                      "rng_after": rng_after, "node_type": tt[1], "edge_time": tt[2], "edge_index": tt[3],
+                      "edge_type": tt[4]})
+    plain = {t: {s_: {r: {tid: dict(adl) for tid, adl in tesr.items()} for r, tesr in d2.items()}
+                 for s_, d2 in d1.items()} for t, d1 in g.edge_list.items()}
+    fx = {"edge_list": plain, "types": g.get_types(), "meta_graph": g.get_meta_graph(), "time_range": time_range,
+          "inp": inp, "cases": cases}
+    path = os.path.join(OUT_DIR, name + ".pt")
+    torch.save(fx, path)
+    print("%-28s %d sampled cases  %.0f KB" % (name, len(cases), os.path.getsize(path) / 1024))
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     to_torch_case("to_torch", seed=31)
+    sampler_case("sampler", seed=3)
     c1 = synth.make_c1()
     conv_case("c1_norte", c1, 64, 4, True, False, seed=10)              # BASELINE config 1
     conv_case("c1_rte", c1, 64, 4, True, True, seed=11, grads=True)

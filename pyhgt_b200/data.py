@@ -14,6 +14,8 @@ launches only.
 import numpy as np
 import torch
 
+from .sampler import FrozenGraph, sample_subgraph  # noqa: F401  (data.py:87 lives next to to_torch in the reference)
+
 
 def to_torch(feature, time, edge_list, graph, device=None, prebuild_plan=False, num_relations=None):
     """Returns (node_feature, node_type, edge_time, edge_index, edge_type, node_dict, edge_dict) exactly like the

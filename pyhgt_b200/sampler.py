@@ -1,0 +1,278 @@
+"""HGSampling — the budget sampler that feeds the hot path (reference: pyHGT/data.py:87-210 ``sample_subgraph``;
+SURVEY.md §8(f) rank 4).  Host-side by nature (a sequential budget process driven by numpy's global RNG); this version
+keeps the reference's semantics EXACTLY — the same draws from numpy's global RNG in the same order, the same
+dict-iteration orders — so that with the same seed it returns the same ``(feature, times, edge_list, indxs, texts)``,
+and ``to_torch`` then emits the same tensors.  What changes is the data structure:
+
+  * ``FrozenGraph`` — the reference's 5-level ``edge_list[target_type][source_type][relation][target_id][source_id] =
+    time`` dict-of-dicts flattened ONCE into CSR arrays per <target type, source type, relation> (neighbour ids and times
+    in dict insertion order, id -> row map), the form a device-side ingest would consume;
+  * the budget ``{source_id: [score, time]}`` per type becomes three flat arrays (score, time, insertion stamp) — the
+    insertion stamp reproduces ``list(budget.keys())`` order, including pop-and-re-insert;
+  * the final "reconstruct the sampled adjacency" triple loop (data.py:190-209: every sampled target x every neighbour,
+    membership tests in Python dicts) becomes one gather + mask per <target type, source type, relation>.
+
+The sampled ``edge_list`` values are ``[E_block, 2]`` int64 arrays of ``[target_ser, source_ser]`` rows (the reference
+builds Python lists of pairs with the same content and order); ``pyhgt_b200.data.to_torch`` and the reference's
+``to_torch`` accept both.
+"""
+from collections import defaultdict
+
+import numpy as np
+
+_NO_TIME = np.iinfo(np.int64).min          # stands for `None` in the neighbour-time arrays (data.py:121-123)
+
+
+class _Block:
+    """One <target type, source type, relation> adjacency in CSR form, dict insertion order preserved."""
+    __slots__ = ("row_of", "ptr", "nbr", "time", "has_none")
+
+    def __init__(self, tesr, n_target_ids):
+        keys = list(tesr.keys())
+        self.row_of = np.full(n_target_ids, -1, dtype=np.int64)
+        counts = np.fromiter((len(tesr[k]) for k in keys), dtype=np.int64, count=len(keys))
+        self.ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        if keys:
+            self.row_of[np.asarray(keys, dtype=np.int64)] = np.arange(len(keys), dtype=np.int64)
+        total = int(self.ptr[-1])
+        self.nbr = np.empty(total, dtype=np.int64)
+        self.time = np.empty(total, dtype=np.int64)
+        has_none = False
+        pos = 0
+        for k in keys:
+            adl = tesr[k]
+            n = len(adl)
+            self.nbr[pos:pos + n] = np.fromiter(adl.keys(), dtype=np.int64, count=n)
+            vals = list(adl.values())
+            if any(v is None for v in vals):
+                has_none = True
+                vals = [_NO_TIME if v is None else v for v in vals]
+            self.time[pos:pos + n] = np.asarray(vals, dtype=np.int64)
+            pos += n
+        self.has_none = has_none
+
+    def row(self, target_id):
+        if target_id < 0 or target_id >= self.row_of.shape[0]:
+            return -1
+        return int(self.row_of[target_id])
+
+
+class FrozenGraph:
+    """CSR snapshot of a reference ``Graph`` (pyHGT/data.py:19-84).  Keeps the dict iteration orders the sampler's
+    results depend on: target types, source types per target type, relations per pair."""
+
+    def __init__(self, graph):
+        self.graph = graph
+        n_ids = defaultdict(int)
+        for t_t, d1 in graph.edge_list.items():
+            for s_t, d2 in d1.items():
+                for r, tesr in d2.items():
+                    for tid, adl in tesr.items():
+                        if tid + 1 > n_ids[t_t]:
+                            n_ids[t_t] = tid + 1
+                        if adl:
+                            m = max(adl.keys()) + 1
+                            if m > n_ids[s_t]:
+                                n_ids[s_t] = m
+        self.n_ids = dict(n_ids)
+        self.blocks = {}                                  # target_type -> source_type -> relation -> _Block (ordered)
+        for t_t, d1 in graph.edge_list.items():
+            self.blocks[t_t] = {}
+            for s_t, d2 in d1.items():
+                self.blocks[t_t][s_t] = {}
+                for r, tesr in d2.items():
+                    self.blocks[t_t][s_t][r] = _Block(tesr, self.n_ids.get(t_t, 0))
+
+    def ensure_ids(self, _type, max_id):
+        if max_id + 1 > self.n_ids.get(_type, 0):
+            self.n_ids[_type] = max_id + 1
+
+
+class _TypeState:
+    """layer_data[type] and budget[type] of the reference as flat arrays over node ids."""
+
+    def __init__(self, n):
+        self.in_layer = np.zeros(n, dtype=bool)
+        self.ser = np.full(n, -1, dtype=np.int64)
+        self.layer_time = np.zeros(n, dtype=np.int64)
+        self.layer_ids = []                                # insertion order == ser order
+        self.in_budget = np.zeros(n, dtype=bool)
+        self.score = np.zeros(n, dtype=np.float64)
+        self.b_time = np.zeros(n, dtype=np.int64)
+        self.stamp = np.zeros(n, dtype=np.int64)
+
+    def grow(self, n):
+        if n <= self.in_layer.shape[0]:
+            return
+        def ext(a, fill):
+            b = np.full(n, fill, dtype=a.dtype)
+            b[:a.shape[0]] = a
+            return b
+        self.in_layer = ext(self.in_layer, False)
+        self.ser = ext(self.ser, -1)
+        self.layer_time = ext(self.layer_time, 0)
+        self.in_budget = ext(self.in_budget, False)
+        self.score = ext(self.score, 0.0)
+        self.b_time = ext(self.b_time, 0)
+        self.stamp = ext(self.stamp, 0)
+
+
+def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=None, feature_extractor=None):
+    """Drop-in for pyHGT/data.py:87 ``sample_subgraph``.  `graph` is a reference ``Graph`` or a ``FrozenGraph`` of it
+    (freeze once, sample many batches).  Consumes numpy's global RNG exactly like the reference."""
+    fg = graph if isinstance(graph, FrozenGraph) else FrozenGraph(graph)
+    ref_graph = fg.graph
+    max_time = np.max(list(time_range.keys()))
+    states = {}                       # per type arrays
+    layer_order = []                  # key order of the reference's `layer_data` defaultdict
+    budget_order = []                 # key order of the reference's `budget` defaultdict
+    stamp_counter = [0]
+
+    def state(_type, touch_layer=False):
+        st = states.get(_type)
+        if st is None:
+            st = states[_type] = _TypeState(fg.n_ids.get(_type, 0))
+        if touch_layer and _type not in layer_seen:
+            layer_seen.add(_type)
+            layer_order.append(_type)
+        return st
+
+    layer_seen = set()
+    budget_seen = set()
+
+    def add_layer(_type, _id, _time):
+        st = state(_type, touch_layer=True)
+        if _id >= st.in_layer.shape[0]:
+            fg.ensure_ids(_type, _id)
+            st.grow(fg.n_ids[_type])
+        st.ser[_id] = len(st.layer_ids)                   # re-adding an id overwrites [ser, time] (dict semantics)
+        if not st.in_layer[_id]:
+            st.layer_ids.append(_id)
+        st.in_layer[_id] = True
+        st.layer_time[_id] = _time
+
+    def add_budget(target_type, target_id, target_time):
+        te = fg.blocks.get(target_type)
+        if te is None:
+            return
+        for source_type, tes in te.items():               # data.py:113
+            for relation_type, blk in tes.items():        # data.py:115
+                if relation_type == 'self':
+                    continue
+                row = blk.row(target_id)
+                if row < 0:
+                    continue
+                a, b = int(blk.ptr[row]), int(blk.ptr[row + 1])
+                n_adl = b - a
+                if n_adl < sampled_number:                # data.py:119-122
+                    ids = blk.nbr[a:b]
+                    tms = blk.time[a:b]
+                else:
+                    # == np.random.choice(list(adl.keys()), sampled_number, replace=False): RandomState.choice draws
+                    # permutation(len(a))[:size] whether `a` is the population or its size, so the stream is the same
+                    pos = np.random.choice(n_adl, sampled_number, replace=False)
+                    ids = blk.nbr[a:b][pos]
+                    tms = blk.time[a:b][pos]
+                n_s = ids.shape[0]
+                if n_s == 0:
+                    continue
+                if blk.has_none:
+                    tms = np.where(tms == _NO_TIME, target_time, tms)
+                late = tms > max_time                     # data.py:126 (short-circuit `or`: layer_data[source_type] is
+                if late.all():                            # only touched when some candidate passes the time test)
+                    continue
+                st = state(source_type, touch_layer=True)
+                if int(ids.max()) >= st.in_layer.shape[0]:
+                    fg.ensure_ids(source_type, int(ids.max()))
+                    st.grow(fg.n_ids[source_type])
+                keep = ~late & ~st.in_layer[ids]
+                if not keep.any():
+                    continue
+                if source_type not in budget_seen:        # budget[source_type] is created by its first real update
+                    budget_seen.add(source_type)
+                    budget_order.append(source_type)
+                kid, ktm = ids[keep], tms[keep]
+                new = ~st.in_budget[kid]
+                n_new = int(new.sum())
+                if n_new:
+                    st.stamp[kid[new]] = stamp_counter[0] + np.arange(n_new)
+                    stamp_counter[0] += n_new
+                    st.in_budget[kid[new]] = True
+                    st.score[kid[new]] = 0.0
+                st.score[kid] += 1.0 / n_s                # data.py:128 (ids are unique inside one adjacency)
+                st.b_time[kid] = ktm                      # data.py:129
+
+    # first adding the sampled nodes then updating budget (data.py:134-140)
+    for _type in inp:
+        for _id, _time in inp[_type]:
+            add_layer(_type, _id, _time)
+    for _type in inp:
+        for _id, _time in inp[_type]:
+            add_budget(_type, _id, _time)
+
+    for _layer in range(sampled_depth):                   # data.py:146
+        for source_type in list(budget_order):
+            st = states[source_type]
+            cand = np.nonzero(st.in_budget)[0]
+            keys = cand[np.argsort(st.stamp[cand], kind="stable")]          # == list(budget[source_type].keys())
+            if sampled_number > len(keys):
+                sampled_ids = np.arange(len(keys))
+            else:
+                score = st.score[keys] ** 2
+                score = score / np.sum(score)
+                sampled_ids = np.random.choice(len(score), sampled_number, p=score, replace=False)
+            sampled_keys = keys[sampled_ids]
+            for k in sampled_keys:                        # data.py:166-167
+                add_layer(source_type, int(k), int(st.b_time[k]))
+            for k in sampled_keys:                        # data.py:168-170
+                add_budget(source_type, int(k), int(st.b_time[k]))
+                st.in_budget[k] = False                   # budget[source_type].pop(k)
+
+    # hand the reference-shaped layer_data to the feature extractor (data.py:174)
+    layer_data = defaultdict(lambda: {})
+    for _type in layer_order:
+        st = states[_type]
+        d = layer_data[_type]
+        for _id in st.layer_ids:
+            d[_id] = [int(st.ser[_id]), int(st.layer_time[_id])]
+    feature, times, indxs, texts = feature_extractor(layer_data, ref_graph)
+
+    edge_list = defaultdict(lambda: defaultdict(lambda: defaultdict(lambda: [])))
+    for _type in layer_order:                             # data.py:181-184 'self' loops
+        st = states[_type]
+        n = len(st.layer_ids)
+        if n:
+            sers = st.ser[np.asarray(st.layer_ids, dtype=np.int64)]
+            edge_list[_type][_type]['self'] = np.stack([sers, sers], 1)
+    # reconstruct the sampled adjacency (data.py:190-209), one gather + mask per block
+    for target_type, te in fg.blocks.items():
+        tst = states.get(target_type)
+        if tst is None or not tst.layer_ids:
+            continue
+        tids = np.asarray(tst.layer_ids, dtype=np.int64)
+        for source_type, tes in te.items():
+            sst = states.get(source_type)
+            if sst is None or not sst.layer_ids:
+                continue
+            for relation_type, blk in tes.items():
+                rows = blk.row_of[tids[tids < blk.row_of.shape[0]]]
+                tsel = tids[tids < blk.row_of.shape[0]][rows >= 0]
+                rows = rows[rows >= 0]
+                if rows.size == 0:
+                    continue
+                a, b = blk.ptr[rows], blk.ptr[rows + 1]
+                cnt = b - a
+                total = int(cnt.sum())
+                if total == 0:
+                    continue
+                owner = np.repeat(np.arange(rows.size), cnt)
+                offs = np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+                nb = blk.nbr[a[owner] + offs]
+                ok = nb < sst.in_layer.shape[0]
+                ok[ok] = sst.in_layer[nb[ok]]
+                if not ok.any():
+                    continue
+                pairs = np.stack([tst.ser[tsel[owner[ok]]], sst.ser[nb[ok]]], 1)
+                cur = edge_list[target_type][source_type][relation_type]
+                edge_list[target_type][source_type][relation_type] = pairs if len(cur) == 0 else np.concatenate([cur, pairs])
+    return feature, times, edge_list, indxs, texts
