@@ -357,7 +357,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
 }
 
 template <int VEC, int NCH>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(kCtaThreads, (VEC * NCH <= 4) ? 2 : 1)   // narrow rows (d_k <= 16): two CTAs per SM
 k_edge_fwd_tma(EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -661,8 +661,11 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
   const size_t row_bytes = 2 * (size_t)d * 4;
   const size_t slot_bytes = kvr ? 2 * row_bytes : row_bytes;
   if (variant == 0) variant = 2;
+  // narrow rows (one float4 per lane): the kernel is bound by per-destination latency, not by bytes in flight, so two
+  // CTAs share an SM (32 warps) with half the ring each
+  const bool two_ctas = vec * nch <= 4;
   if (variant == 2) {
-    const size_t budget = 200 * 1024;
+    const size_t budget = two_ctas ? 100 * 1024 : 200 * 1024;
     int stages = (int)(budget / (kWarpsPerCta * slot_bytes));
     if (stages > 8) stages = 8;
     if (stages < 2 || row_bytes % 16 != 0) variant = 1;     // rows too wide / misaligned for the ring
@@ -673,6 +676,7 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
   }
   HGT_REQUIRE(variant == 1 || variant == 2, "hgt_edge_forward: unknown variant %d", variant);
   // persistent grid: one CTA per SM, never more CTAs than tiles/warps
+  if (two_ctas && variant == 2) grid = 2 * sms;
   int max_ctas = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   if (grid > max_ctas) grid = max_ctas;
   HGT_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), st));
