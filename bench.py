@@ -483,8 +483,11 @@ def main_ours(args, rank, local_rank, world):
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
+        # claim min(algorithmic bytes, measured DRAM bytes) / t  (tables that fit L2 make B_alg over-count)
+        claim = min(alg, traffic) if traffic else alg
         roofline = {"kernel": "k_edge_fwd_tma (csrc/edge.cu)", "bound": "hbm", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                    "frac_min_alg_traffic": (claim / (edge_med_ms * 1e-3) / 1e9 / hbm_peak) if edge_med_ms > 0 else None,
                     "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                     "avg_launch_ms": edge_med_ms, "launch_ms_stat": "median of %d launches" % len(edge_ms),
                     "share_of_step": edge_med_ms / ms_step if ms_step else None}
