@@ -261,23 +261,36 @@ __global__ void k_halo_pull_split(const float* const* __restrict__ peers, const 
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int MAXV = 8;                                   // float4 chunks per lane held in flight (rows <= 1024 floats)
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const int owner = src_rank[r];
     const float4* src = reinterpret_cast<const float4*>(peers[owner]) + (int64_t)src_row[r] * vec_per_row;
-    for (int c = lane; c < vec_per_row; c += 32) {
-      float4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + c));
-      if (owner == self_rank) out_f32[r * vec_per_row + c] = v;
-      const float f[4] = {v.x, v.y, v.z, v.w};
-      __nv_bfloat16 h[4], l[4];
+    // issue every load of the row before the first conversion: NVLink round trips overlap instead of serialising
+    float4 v[MAXV];
+    for (int c0 = 0; c0 < vec_per_row; c0 += 32 * MAXV) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        h[j] = __float2bfloat16_rn(f[j]);
-        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = c0 + lane + 32 * i;
+        if (c < vec_per_row)
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "l"(src + c));
       }
-      hi[r * vec_per_row + c] = *reinterpret_cast<uint2*>(h);
-      lo[r * vec_per_row + c] = *reinterpret_cast<uint2*>(l);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = c0 + lane + 32 * i;
+        if (c < vec_per_row) {
+          if (owner == self_rank) out_f32[r * vec_per_row + c] = v[i];
+          const float f[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(f[j]);
+            l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+          }
+          hi[r * vec_per_row + c] = *reinterpret_cast<uint2*>(h);
+          lo[r * vec_per_row + c] = *reinterpret_cast<uint2*>(l);
+        }
+      }
     }
   }
 }
