@@ -10,7 +10,7 @@
 // Tensor-core path (tcgen05, sm_100a): the same split-bf16 x3 scheme as the forward (x = hi + lo, three bf16 products
 // in one fp32 TMEM accumulator):
 //   k_act_split / k_split_colsum   fp32 -> bf16 hi/lo (optionally gelu first); the dOut split pass also produces db
-//   k_lin_dx_tc   persistent CTAs, 128 x BN tiles of dA, double-buffered TMEM accumulator; K runs over (column block, 64-wide k-block); A operand = dOut tiles
+//   k_lin_dx_tc   one 128 x BN tile of dA per CTA; K runs over (column block, 64-wide k-block); A operand = dOut tiles
 //                 (K-major), B operand = W^T (a transposed, zero-padded bf16 split of the small weight matrix);
 //                 epilogue: optional `+= dA`, optional `* gelu'(aux)` (the gelu in front of the a_linears, conv.py:119)
 //   k_lin_dw_tc   dW tile [128 of width] x [BN of K_in] per CTA, reduction over a chunk of the group's rows; both operands
@@ -172,16 +172,10 @@ struct DxSched {
   int32_t bn_box;            // rows of the W^T TMA box (n-tile width in shared memory)
 };
 
-// Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...; the accumulator is double-buffered in TMEM
-// (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1; the epilogue transposes 32 x 16 chunks
-// through shared memory so that 4 lanes write 64 contiguous bytes of a row (full sectors).
-constexpr int DX_STG_LD = 20;                         // floats per staged row (16 + 4 pad)
-
 __global__ void __launch_bounds__(BW_THREADS, 1)
 k_lin_dx_tc(const CUtensorMap* __restrict__ maps, int map_wt, const GcTask* __restrict__ tasks,
             const int32_t* __restrict__ group_task0, const hgt_lin_group* __restrict__ groups, int n_groups, int K_in,
-            int width, float* __restrict__ dA, int accumulate, const float* __restrict__ gelu_aux, DxSched sc,
-            int total_tiles) {
+            int width, float* __restrict__ dA, int accumulate, const float* __restrict__ gelu_aux, DxSched sc) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr int STAGES = 2;
@@ -190,28 +184,33 @@ k_lin_dx_tc(const CUtensorMap* __restrict__ maps, int map_wt, const GcTask* __re
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;      // A_hi, A_lo, B_hi, B_lo
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;                    // [2] accumulator complete
-  uint64_t* tempty_bar = tfull_bar + 2;                        // [2] accumulator drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* stg_all = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [4 warps][32][DX_STG_LD]
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x, g = 0;
+  while (g + 1 < n_groups && tile >= sc.first_tile[g + 1]) ++g;
+  const hgt_lin_group grp = groups[g];
+  const int local = tile - sc.first_tile[g];
+  const int mt = local / sc.n_tiles_n, nt = local - mt * sc.n_tiles_n;
+  const int64_t m0 = (int64_t)mt * 128;
+  const int n0 = nt * 256;
+  const int bn = min(256, K_in - n0);                           // multiple of 16
   const int kb_per_c = (width + BK - 1) / BK;
+  const int total_iters = grp.n_cblocks * kb_per_c;
+  const int task0 = group_task0[g];
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(s_u32(&full_bar[s]), 1);
       mbar_init(s_u32(&empty_bar[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_u32(&tfull_bar[b]), 1);
-      mbar_init(s_u32(&tempty_bar[b]), 4);                       // one arrival per epilogue warp
-    }
+    mbar_init(s_u32(tmem_full_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
-                 "r"(512u) : "memory");
+                 "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -219,148 +218,92 @@ k_lin_dx_tc(const CUtensorMap* __restrict__ maps, int map_wt, const GcTask* __re
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // tile -> (group, m-tile, n-tile); every role walks the same sequence
-  auto decode = [&](int tile, int& g, int& mt, int& nt) {
-    g = 0;
-    while (g + 1 < n_groups && tile >= sc.first_tile[g + 1]) ++g;
-    const int local = tile - sc.first_tile[g];
-    mt = local / sc.n_tiles_n;
-    nt = local - mt * sc.n_tiles_n;
-  };
-
   if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* m_wt_hi = maps + map_wt;
       const CUtensorMap* m_wt_lo = maps + map_wt + 1;
       map_acquire(m_wt_hi);
       map_acquire(m_wt_lo);
-      int last_g = -1;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int g, mt, nt;
-        decode(tile, g, mt, nt);
-        const int n_cb = groups[g].n_cblocks;
-        const int task0 = group_task0[g];
-        if (g != last_g) {
-          for (int c = 0; c < n_cb; ++c) {
-            map_acquire(maps + tasks[task0 + c].map_dout);
-            map_acquire(maps + tasks[task0 + c].map_dout + 1);
-          }
-          last_g = g;
-        }
-        const int m0 = mt * 128, n0 = nt * 256;
-        const int iters = n_cb * kb_per_c;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(s_u32(&empty_bar[s]), ph ^ 1u);
-          const int c = i / kb_per_c, kb = i - c * kb_per_c;
-          const GcTask tk = tasks[task0 + c];
-          const CUtensorMap* m_hi = maps + tk.map_dout;
-          const CUtensorMap* m_lo = m_hi + 1;
-          const uint32_t bar = s_u32(&full_bar[s]);
-          const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
-          mbar_expect_tx(bar, stage_bytes);
-          tma_load_2d(sa, m_hi, kb * BK, m0, bar);
-          tma_load_2d(sa + ATOM_BYTES, m_hi, kb * BK, m0 + 64, bar);
-          tma_load_2d(sa + a_bytes, m_lo, kb * BK, m0, bar);
-          tma_load_2d(sa + a_bytes + ATOM_BYTES, m_lo, kb * BK, m0 + 64, bar);
-          tma_load_2d(sa + 2 * a_bytes, m_wt_hi, tk.wt_col0 + kb * BK, n0, bar);
-          tma_load_2d(sa + 2 * a_bytes + b_bytes, m_wt_lo, tk.wt_col0 + kb * BK, n0, bar);
-        }
+      for (int c = 0; c < grp.n_cblocks; ++c) {
+        map_acquire(maps + tasks[task0 + c].map_dout);
+        map_acquire(maps + tasks[task0 + c].map_dout + 1);
+      }
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(s_u32(&empty_bar[s]), ph ^ 1u);
+        const int c = it / kb_per_c, kb = it - c * kb_per_c;
+        const GcTask tk = tasks[task0 + c];
+        const CUtensorMap* m_hi = maps + tk.map_dout;
+        const CUtensorMap* m_lo = m_hi + 1;
+        const uint32_t bar = s_u32(&full_bar[s]);
+        const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+        mbar_expect_tx(bar, stage_bytes);
+        tma_load_2d(sa, m_hi, kb * BK, (int)m0, bar);
+        tma_load_2d(sa + ATOM_BYTES, m_hi, kb * BK, (int)m0 + 64, bar);
+        tma_load_2d(sa + a_bytes, m_lo, kb * BK, (int)m0, bar);
+        tma_load_2d(sa + a_bytes + ATOM_BYTES, m_lo, kb * BK, (int)m0 + 64, bar);
+        tma_load_2d(sa + 2 * a_bytes, m_wt_hi, tk.wt_col0 + kb * BK, n0, bar);
+        tma_load_2d(sa + 2 * a_bytes + b_bytes, m_wt_lo, tk.wt_col0 + kb * BK, n0, bar);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        int g, mt, nt;
-        decode(tile, g, mt, nt);
-        const int bn = min(256, K_in - nt * 256);
-        const uint32_t idesc = idesc_bf16(128, bn, false, false);
-        const int iters = groups[g].n_cblocks * kb_per_c;
-        const uint32_t buf = ti & 1u;
-        mbar_wait(s_u32(&tempty_bar[buf]), ((ti >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+      const uint32_t idesc = idesc_bf16(128, bn, false, false);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(s_u32(&full_bar[s]), ph);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * 256u;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(s_u32(&full_bar[s]), ph);
-          tc_fence_after();
-          const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = desc_k_sw128(sa), a_lo = desc_k_sw128(sa + a_bytes);
-          const uint64_t b_hi = desc_k_sw128(sa + 2 * a_bytes), b_lo = desc_k_sw128(sa + 2 * a_bytes + b_bytes);
+        const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t a_hi = desc_k_sw128(sa), a_lo = desc_k_sw128(sa + a_bytes);
+        const uint64_t b_hi = desc_k_sw128(sa + 2 * a_bytes), b_lo = desc_k_sw128(sa + 2 * a_bytes + b_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t o = (uint64_t)(2 * k);                 // +32 bytes inside the swizzle row
-            umma_bf16_ss(tacc, a_hi + o, b_hi + o, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16_ss(tacc, a_hi + o, b_lo + o, idesc, 1u);
-            umma_bf16_ss(tacc, a_lo + o, b_hi + o, idesc, 1u);
-          }
-          umma_commit(s_u32(&empty_bar[s]));
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t o = (uint64_t)(2 * k);                 // +32 bytes inside the swizzle row
+          umma_bf16_ss(tmem_base, a_hi + o, b_hi + o, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base, a_hi + o, b_lo + o, idesc, 1u);
+          umma_bf16_ss(tmem_base, a_lo + o, b_hi + o, idesc, 1u);
         }
-        umma_commit(s_u32(&tfull_bar[buf]));
+        umma_commit(s_u32(&empty_bar[s]));
       }
+      umma_commit(s_u32(tmem_full_bar));
     }
   } else {
     const int lg = warp & 3;                                     // TMEM lane quarter this warp may read
-    float* stg = stg_all + (size_t)(warp - 2) * 32 * DX_STG_LD;
-    const int sub = lane & 3, rsel = lane >> 2;
-    uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      int g, mt, nt;
-      decode(tile, g, mt, nt);
-      const hgt_lin_group grp = groups[g];
-      const int64_t m0 = (int64_t)mt * 128;
-      const int n0 = nt * 256;
-      const int bn = min(256, K_in - n0);
-      const uint32_t buf = ti & 1u;
-      mbar_wait(s_u32(&tfull_bar[buf]), (ti >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + buf * 256u + ((uint32_t)(lg * 32) << 16);
-      const int64_t slab_row0 = grp.a_row0 + m0 + lg * 32;         // first global row of this warp's 32-row slab
-      const int64_t rows_left = grp.m - (m0 + lg * 32);            // valid rows in the slab (may be <= 0)
-      const bool has_work = grp.n_cblocks > 0;
-      for (int c0 = 0; c0 < bn; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_row + (uint32_t)c0, r);
-        tmem_ld_wait();
+    const int row = lg * 32 + lane;
+    mbar_wait(s_u32(tmem_full_bar), 0);
+    tc_fence_after();
+    const bool row_ok = total_iters > 0 && m0 + row < grp.m;
+    const int64_t grow = grp.a_row0 + m0 + row;
+    float* orow = dA + grow * K_in + n0;
+    const float* xrow = gelu_aux ? gelu_aux + grow * K_in + n0 : nullptr;
+    for (int c = 0; c < bn; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<uint4*>(stg + lane * DX_STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        __syncwarp();
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(stg + (8 * k + rsel) * DX_STG_LD + sub * 4);
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rr = 8 * k + rsel;
-          if (has_work && rr < rows_left) {
-            const int64_t off = (slab_row0 + rr) * K_in + n0 + c0 + sub * 4;
-            float4 w = v[k];
-            if (gelu_aux) {
-              const float4 x = *reinterpret_cast<const float4*>(gelu_aux + off);
-              w.x *= gelu_grad(x.x); w.y *= gelu_grad(x.y); w.z *= gelu_grad(x.z); w.w *= gelu_grad(x.w);
-            }
-            if (accumulate) {
-              const float4 o = *reinterpret_cast<const float4*>(dA + off);
-              w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w;
-            }
-            *reinterpret_cast<float4*>(dA + off) = w;
+        for (int j = 0; j < 16; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (xrow) {
+            const float4 x = *reinterpret_cast<const float4*>(xrow + c + j);
+            v.x *= gelu_grad(x.x); v.y *= gelu_grad(x.y); v.z *= gelu_grad(x.z); v.w *= gelu_grad(x.w);
           }
+          if (accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(orow + c + j);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(orow + c + j) = v;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tempty_bar[buf])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -876,14 +819,12 @@ extern "C" int hgt_typed_linear_bwd(const float* dout, const void* dout_hi, cons
     }
     sc.first_tile[n_groups] = (int32_t)total;
     if (total > 0) {
-      const size_t smem = 1024 + 2 * (size_t)(2 * 128 * BK * 2 + 2 * bn_box * BK * 2) + 8 * 8 + 16 +
-                          4 * 32 * DX_STG_LD * sizeof(float) + 64;
+      const size_t smem = 1024 + 2 * (size_t)(2 * 128 * BK * 2 + 2 * bn_box * BK * 2) + 8 * 8 + 16;
       HGT_CHECK_CUDA(cudaFuncSetAttribute(k_lin_dx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // the task table for dX only needs map indices / wt_col0 (already set); first_unit is unused here
       if (have_dsplit && (rc = upload_tasks())) return rc;
-      const int grid = (int)std::min<int64_t>(total, hgt_sm_count());
-      k_lin_dx_tc<<<grid, BW_THREADS, smem, st>>>(d_maps, map_wt, d_tasks, d_gt0, groups, n_groups, K, cb_width, dA,
-                                                  accumulate_dA, gelu_aux, sc, (int)total);
+      k_lin_dx_tc<<<(unsigned)total, BW_THREADS, smem, st>>>(d_maps, map_wt, d_tasks, d_gt0, groups, n_groups, K, cb_width,
+                                                             dA, accumulate_dA, gelu_aux, sc);
       HGT_LAUNCH_CHECK();
     }
   }
