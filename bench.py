@@ -398,9 +398,12 @@ def main_ours(args, rank, local_rank, world):
         n_dst_local, e_local = N, E
     else:
         from pyhgt_b200 import sharded
+        torch.zeros(1, device=dev)
+        torch.cuda.synchronize()                      # context / allocator start-up is not part of the partition time
         t0 = time.perf_counter()
         shard = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, g.edge_time if RTE else None, TYPES,
                                            RELS, rank, world, dev, halo_mode=args.halo)
+        torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
         x_own = x_host[shard.owned_global].to(dev)
 
