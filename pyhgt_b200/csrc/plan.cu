@@ -255,32 +255,45 @@ __global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_
 
 // Pull + convert: the halo rows are only ever consumed as the bf16 hi/lo operand split of the projection GEMM, so the
 // conversion is done while the row crosses NVLink; fp32 is kept only for the rows this rank owns (skip connection).
-__global__ void k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
-                                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank,
-                                  float4* __restrict__ out_f32, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+template <int VPL>   // float4 chunks per lane and row (row = 32 * VPL float4 at most)
+__global__ void __launch_bounds__(256)
+k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
+                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank,
+                  float4* __restrict__ out_f32, uint2* __restrict__ hi, uint2* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  constexpr int MAXV = 8;                                   // float4 chunks per lane held in flight (rows <= 1024 floats)
-  for (int64_t r = warp; r < n_rows; r += n_warps) {
-    const int owner = src_rank[r];
-    const float4* src = reinterpret_cast<const float4*>(peers[owner]) + (int64_t)src_row[r] * vec_per_row;
-    // issue every load of the row before the first conversion: NVLink round trips overlap instead of serialising
-    float4 v[MAXV];
-    for (int c0 = 0; c0 < vec_per_row; c0 += 32 * MAXV) {
+  constexpr int RB = (VPL <= 2) ? 4 : (VPL <= 4 ? 2 : 1);   // rows per pass: every load of RB rows is in flight before the
+                                                            // first conversion, so NVLink round trips overlap
+  for (int64_t r0 = warp * RB; r0 < n_rows; r0 += n_warps * RB) {
+    float4 v[RB][VPL];
+    int owner[RB];
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = c0 + lane + 32 * i;
-        if (c < vec_per_row)
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "l"(src + c));
+    for (int b = 0; b < RB; ++b) {
+      const int64_t r = r0 + b;
+      owner[b] = -1;
+      if (r < n_rows) {
+        owner[b] = src_rank[r];
+        const float4* src = reinterpret_cast<const float4*>(peers[owner[b]]) + (int64_t)src_row[r] * vec_per_row;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int c = lane + 32 * i;
+          if (c < vec_per_row)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v[b][i].x), "=f"(v[b][i].y), "=f"(v[b][i].z), "=f"(v[b][i].w) : "l"(src + c));
+        }
       }
+    }
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = c0 + lane + 32 * i;
+    for (int b = 0; b < RB; ++b) {
+      const int64_t r = r0 + b;
+      if (r >= n_rows) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = lane + 32 * i;
         if (c < vec_per_row) {
-          if (owner == self_rank) out_f32[r * vec_per_row + c] = v[i];
-          const float f[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          if (owner[b] == self_rank) out_f32[r * vec_per_row + c] = v[b][i];
+          const float f[4] = {v[b][i].x, v[b][i].y, v[b][i].z, v[b][i].w};
           __nv_bfloat16 h[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -467,9 +480,17 @@ extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_ra
   int64_t blocks = (n_rows + warps_per_block - 1) / warps_per_block;
   int64_t cap = (int64_t)hgt_sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  k_halo_pull_split<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(
-      reinterpret_cast<const float* const*>(peer_ptrs_dev), src_rank, src_row, n_rows, width / 4, self_rank,
-      reinterpret_cast<float4*>(out_f32), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  const int vpr = width / 4;
+  HGT_REQUIRE(vpr <= 256, "hgt_halo_pull_split: rows of more than 1024 floats are not supported (width=%d)", width);
+  auto pf = reinterpret_cast<const float* const*>(peer_ptrs_dev);
+  auto o4 = reinterpret_cast<float4*>(out_f32);
+  auto h2 = reinterpret_cast<uint2*>(hi);
+  auto l2 = reinterpret_cast<uint2*>(lo);
+  const unsigned g = (unsigned)blocks, t = warps_per_block * 32;
+  if (vpr <= 32) k_halo_pull_split<1><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
+  else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
+  else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
+  else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
   HGT_LAUNCH_CHECK();
   return 0;
 }

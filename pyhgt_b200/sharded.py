@@ -289,9 +289,11 @@ class ShardedGraph:
             # fused pull + bf16 hi/lo conversion: halo rows never exist in fp32 on this rank
             hi = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
             lo = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
-            _lib.call("hgt_halo_pull_split", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(),
-                      n_local, d, self.rank, x_local.data_ptr(), hi.data_ptr(), lo.data_ptr(),
-                      torch.cuda.current_stream().cuda_stream)
+            from .conv import HGTConv
+            with HGTConv._stage("halo_pull_kernel"):               # bench.py: the kernel alone, without barriers / publish
+                _lib.call("hgt_halo_pull_split", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(),
+                          self.pull_row.data_ptr(), n_local, d, self.rank, x_local.data_ptr(), hi.data_ptr(),
+                          lo.data_ptr(), torch.cuda.current_stream().cuda_stream)
             return x_local, (hi, lo)
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
                   x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
