@@ -405,7 +405,10 @@ def main_ours(args, rank, local_rank, world):
                                            RELS, rank, world, dev, halo_mode=args.halo)
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
-        x_own = x_host[shard.owned_global].to(dev)
+        # the layer input lives in the rank's NVLink-mapped publish area (where a previous layer's epilogue would have
+        # written it): no publish copy inside the step
+        x_own = shard.input_buffer(D, 0)
+        x_own.copy_(x_host[shard.owned_global].to(dev))
 
         def step():
             return shard.forward(conv, x_own)

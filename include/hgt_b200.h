@@ -101,15 +101,18 @@ int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_rows, int32_
 
 /* Multi-GPU halo exchange fused into one kernel: out[i,:] = peer[src_rank[i]][src_row[i],:], where
  * peer_ptrs_dev is the DEVICE address of an array of world_size device pointers to every rank's [rows,width]
- * feature buffer (NVLink peer mappings, e.g. torch symmetric memory `buffer_ptrs_dev`).  The caller orders the
- * ranks (publish -> barrier -> pull -> barrier).  width % 4 == 0. */
+ * feature buffer (NVLink peer mappings, e.g. torch symmetric memory `buffer_ptrs_dev`); `row_base` is added to every
+ * src_row (double-buffered publish areas inside one symmetric allocation).  The caller orders the ranks: publish ->
+ * barrier -> pull; with two publish areas used alternately that ONE barrier per exchange also guarantees that nobody
+ * still reads the area about to be overwritten.  width % 4 == 0. */
 int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
-                  int32_t width, float* out, void* stream);
+                  int32_t width, int64_t row_base, float* out, void* stream);
 /* Same pull fused with the operand conversion of the projection GEMM: every row is written as the bf16 hi/lo split
  * (hi/lo [n_rows, width], the A operand of hgt_typed_linear_presplit) while it crosses NVLink; the fp32 copy is kept
  * only for rows owned by `self_rank` (the update epilogue's skip connection reads those).  width % 8 == 0. */
 int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
-                        int32_t width, int32_t self_rank, float* out_f32, void* hi, void* lo, void* stream);
+                        int32_t width, int32_t self_rank, int64_t row_base, float* out_f32, void* hi, void* lo,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Typed (per-node-type) linear layers — "per-type linear dispatch" (conv.py:73-77,96-97,103,125).

@@ -236,13 +236,13 @@ __global__ void k_gather_rows_scalar(const float* __restrict__ in, const int32_t
 
 // Fused halo exchange: one warp per destination row pulls it from the owner's HBM (NVLink peer mapping).
 __global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
-                            const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row,
+                            const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int64_t row_base,
                             float4* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < n_rows; r += n_warps) {
-    const float4* src = reinterpret_cast<const float4*>(peers[src_rank[r]]) + (int64_t)src_row[r] * vec_per_row;
+    const float4* src = reinterpret_cast<const float4*>(peers[src_rank[r]]) + (row_base + src_row[r]) * vec_per_row;
     float4* dst = out + r * vec_per_row;
     for (int c = lane; c < vec_per_row; c += 32) {
       float4 v;
@@ -258,7 +258,7 @@ __global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_
 template <int VPL>   // float4 chunks per lane and row (row = 32 * VPL float4 at most)
 __global__ void __launch_bounds__(256)
 k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
-                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank,
+                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank, int64_t row_base,
                   float4* __restrict__ out_f32, uint2* __restrict__ hi, uint2* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -274,7 +274,7 @@ k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restr
       owner[b] = -1;
       if (r < n_rows) {
         owner[b] = src_rank[r];
-        const float4* src = reinterpret_cast<const float4*>(peers[owner[b]]) + (int64_t)src_row[r] * vec_per_row;
+        const float4* src = reinterpret_cast<const float4*>(peers[owner[b]]) + (row_base + src_row[r]) * vec_per_row;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
           const int c = lane + 32 * i;
@@ -454,7 +454,7 @@ extern "C" int hgt_gather_rows(const float* in, const int32_t* perm, int64_t n_r
 }
 
 extern "C" int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
-                             int32_t width, float* out, void* stream_) {
+                             int32_t width, int64_t row_base, float* out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(width % 4 == 0, "hgt_halo_pull: row width %d must be a multiple of 4 floats", width);
   if (n_rows == 0) return 0;
@@ -463,15 +463,15 @@ extern "C" int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, co
   int64_t cap = (int64_t)hgt_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   k_halo_pull<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(reinterpret_cast<const float* const*>(peer_ptrs_dev),
-                                                                 src_rank, src_row, n_rows, width / 4,
+                                                                 src_rank, src_row, n_rows, width / 4, row_base,
                                                                  reinterpret_cast<float4*>(out));
   HGT_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row,
-                                   int64_t n_rows, int32_t width, int32_t self_rank, float* out_f32, void* hi, void* lo,
-                                   void* stream_) {
+                                   int64_t n_rows, int32_t width, int32_t self_rank, int64_t row_base, float* out_f32,
+                                   void* hi, void* lo, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(width % 8 == 0, "hgt_halo_pull_split: row width %d must be a multiple of 8 floats", width);
   HGT_REQUIRE(out_f32 && hi && lo, "hgt_halo_pull_split: NULL output");
@@ -487,10 +487,10 @@ extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_ra
   auto h2 = reinterpret_cast<uint2*>(hi);
   auto l2 = reinterpret_cast<uint2*>(lo);
   const unsigned g = (unsigned)blocks, t = warps_per_block * 32;
-  if (vpr <= 32) k_halo_pull_split<1><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
-  else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
-  else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
-  else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, o4, h2, l2);
+  if (vpr <= 32) k_halo_pull_split<1><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -96,6 +96,7 @@ class ShardedGraph:
     halo_mode: str = "auto"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer
                                       # memory; "auto": p2p on CUDA when symmetric memory works, else nccl
     _symm: object = None
+    _slot: int = 0
     kv_runs: tuple = None             # (((type, relation), ((row0, row1), ...)), ...) type-relative local rows that need K'/V'
 
     @staticmethod
@@ -266,23 +267,48 @@ class ShardedGraph:
         return self._gather(buf, self.cat_index, self.n_owned + self.n_halo)
 
     def _symm_setup(self, d, device):
+        """One symmetric allocation holding TWO publish areas of max_owned rows each (used alternately)."""
         import torch.distributed._symmetric_memory as symm_mem
         if self._symm is None or self._symm[0].shape[1] != d:
-            buf = symm_mem.empty((max(self.max_owned, 1), d), dtype=torch.float32, device=device)
+            buf = symm_mem.empty((2 * max(self.max_owned, 1), d), dtype=torch.float32, device=device)
             hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
             self._symm = (buf, hdl)
+            self._slot = 0
         return self._symm
+
+    def input_buffer(self, d, slot=0):
+        """[n_owned, d] view of publish area `slot` (0 / 1) in NVLink-mapped symmetric memory: a layer input that lives
+        here needs no publish copy — `forward` recognises it.  A producer alternates the slots from layer to layer (the
+        one barrier of an exchange then also covers the write-after-read hazard).  Plain tensor when the exchange goes
+        through NCCL."""
+        dev = self.device if isinstance(self.device, torch.device) else torch.device(self.device)
+        probe = torch.empty((0, d), dtype=torch.float32, device=dev)
+        self._resolve_halo_mode(probe)
+        if self.halo_mode != "p2p":
+            return torch.empty((self.n_owned, d), dtype=torch.float32, device=dev)
+        buf, _ = self._symm_setup(d, dev)
+        m = max(self.max_owned, 1)
+        return buf[slot * m:slot * m + self.n_owned]
 
     def _exchange_p2p(self, x_own, split=False):
         """Fused halo exchange: every rank publishes x_own in NVLink-mapped symmetric memory and ONE kernel pulls
         each local row (owned and halo alike) straight from its owner's HBM into type-sorted position — no send-side
-        gather, no NCCL call, no re-ordering pass."""
+        gather, no NCCL call, no re-ordering pass.  Two publish areas are used alternately, so ONE barrier per
+        exchange is enough: it says "everybody's rows are published" and, because every rank reaches it only after
+        its previous pull, also "nobody still reads the area written next"."""
         from . import _lib
         d = x_own.shape[1]
         buf, hdl = self._symm_setup(d, x_own.device)
-        hdl.barrier(channel=0)                       # peers finished reading the previous layer's rows
-        buf[:self.n_owned].copy_(x_own)
-        hdl.barrier(channel=1)                       # every rank's rows are published
+        m = max(self.max_owned, 1)
+        slot = -1
+        for k in (0, 1):
+            if x_own.data_ptr() == buf[k * m:].data_ptr() and x_own.is_contiguous():
+                slot = k                                 # already published in place (input_buffer)
+        if slot < 0:
+            slot = self._slot
+            buf[slot * m:slot * m + self.n_owned].copy_(x_own)
+        self._slot = slot ^ 1
+        hdl.barrier(channel=0)                       # every rank's rows are published (and the other area is free)
         n_local = self.n_owned + self.n_halo
         x_local = torch.empty((n_local, d), dtype=torch.float32, device=x_own.device)
         if split and d % 16 == 0 and d >= 64:
@@ -290,13 +316,13 @@ class ShardedGraph:
             hi = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
             lo = torch.empty((n_local, d), dtype=torch.bfloat16, device=x_own.device)
             from .conv import HGTConv
-            with HGTConv._stage("halo_pull_kernel"):               # bench.py: the kernel alone, without barriers / publish
+            with HGTConv._stage("halo_pull_kernel"):               # bench.py: the kernel alone, without barrier / publish
                 _lib.call("hgt_halo_pull_split", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(),
-                          self.pull_row.data_ptr(), n_local, d, self.rank, x_local.data_ptr(), hi.data_ptr(),
+                          self.pull_row.data_ptr(), n_local, d, self.rank, slot * m, x_local.data_ptr(), hi.data_ptr(),
                           lo.data_ptr(), torch.cuda.current_stream().cuda_stream)
             return x_local, (hi, lo)
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
-                  x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                  slot * m, x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return (x_local, None) if split else x_local
 
     def forward_train(self, conv, x_own):
