@@ -80,8 +80,6 @@ class _TypedLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         a, a_act, hi, lo, w_cat = ctx.saved_tensors
-        g_dev, g_host, n_g, _ = ctx.table
-        c_host = ctx.table.c_host
         width = ctx.width
         K = w_cat.shape[1]
         dev = w_cat.device
@@ -93,14 +91,22 @@ class _TypedLinear(torch.autograd.Function):
         db = torch.zeros(w_cat.shape[0], dtype=torch.float32, device=dev) if ctx.has_bias else None
         impl = 2 if ctx.use_tc else 1
         a_f32 = a_act if a_act is not None else a                      # SIMT dW operand (act already applied)
-        wsb = ctypes.c_size_t()
-        _lib.call("hgt_typed_linear_bwd_workspace_bytes", g_host.ctypes.data, n_g, c_host.ctypes.data, K, width, K,
-                  ctx.out_elems, 0, int(hi is not None), impl, ctypes.byref(wsb))
-        ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
-        _lib.call("hgt_typed_linear_bwd", dout.data_ptr(), None, None, ctx.out_elems, _lib.ptr(a_f32), K, _lib.ptr(hi),
-                  _lib.ptr(lo), w_cat.data_ptr(), K, width, g_dev.data_ptr(), g_host.ctypes.data, n_g,
-                  c_host.ctypes.data, _lib.ptr(da), 0, a.data_ptr() if ctx.act else None, dw.data_ptr(), _lib.ptr(db),
-                  impl, ws.data_ptr(), ws.numel(), _stream())
+        # tables whose groups overlap in rows (sharded per-pair compaction) come with disjoint sub-tables: the first call
+        # writes dA, the others accumulate into it; dW / db accumulate anyway
+        tables = getattr(ctx.table, "bwd_tables", None) or [ctx.table]
+        if not ctx.use_tc:
+            tables = [ctx.table]                                       # the SIMT dX uses atomics: overlap is fine
+        for ti, tab in enumerate(tables):
+            g_dev, g_host, n_g, _ = tab
+            c_host = tab.c_host
+            wsb = ctypes.c_size_t()
+            _lib.call("hgt_typed_linear_bwd_workspace_bytes", g_host.ctypes.data, n_g, c_host.ctypes.data, K, width, K,
+                      ctx.out_elems, 0, int(hi is not None), impl, ctypes.byref(wsb))
+            ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+            _lib.call("hgt_typed_linear_bwd", dout.data_ptr(), None, None, ctx.out_elems, _lib.ptr(a_f32), K, _lib.ptr(hi),
+                      _lib.ptr(lo), w_cat.data_ptr(), K, width, g_dev.data_ptr(), g_host.ctypes.data, n_g,
+                      c_host.ctypes.data, _lib.ptr(da), int(ti > 0), a.data_ptr() if ctx.act else None, dw.data_ptr(),
+                      _lib.ptr(db), impl, ws.data_ptr(), ws.numel(), _stream())
         return da, dw, db, None, None, None, None, None, None
 
 
@@ -242,10 +248,10 @@ def typed_linear(a, w_cat, b_cat, table, width, out_elems, impl=0, act=0, zero_r
     return _TypedLinear.apply(a, w_cat, b_cat, table, width, out_elems, impl, act, tuple(zero_ranges))
 
 
-def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time, active=None):
+def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time, active=None, kv_runs=None):
     """`active` (sharded training): active[t] = number of leading nodes of type t (rank order) that are destinations on
     this rank; Q / a_linear / update run for them only, the remaining rows (halo sources) only get K'/V' rows and their
-    output rows stay zero."""
+    output rows stay zero.  `kv_runs`: per-pair row ranges that need K'/V' (plan.layer_tables)."""
     d_in, d, H, T, R = m.in_dim, m.out_dim, m.n_heads, m.num_types, m.num_relations
     plan = _plan.get_plan(node_type, edge_index, edge_type, edge_time if m.use_RTE else None, T, R)
     N, P = plan.n_nodes, plan.n_pairs
@@ -254,7 +260,7 @@ def hgt_conv_autograd(m, node_inp, node_type, edge_index, edge_type, edge_time, 
     x = node_inp if plan.sorted_types else node_inp.index_select(0, plan.perm.long())
     if active is not None and not plan.sorted_types:
         raise ValueError("`active` needs a type-sorted node order")
-    lt = _plan.layer_tables(plan, d_in, d, active)
+    lt = _plan.layer_tables(plan, d_in, d, active, kv_runs)
 
     # 1. relation matrices folded into the typed K/V weights; typed projections -> flat [Q | pad | K'V' table | zero row]
     params = ([l.weight for l in m.q_linears] + [l.bias for l in m.q_linears] +

@@ -398,6 +398,18 @@ def layer_tables(plan, d_in, d_out, active=None, kv_runs=None):
         if len(g2) <= 64 and all((s_, r_) in runs for (s_, r_) in plan.pairs):
             groups, cblocks = g2, c2
     proj = _pack_groups(groups, cblocks, dev)
+    # The backward's dX writes rows non-atomically, so it takes groups with DISJOINT row ranges: split the table into
+    # such subsets (greedy interval colouring; the first subset writes dA, the others accumulate into it).
+    subsets = []
+    for gi, g_ in sorted(enumerate(groups), key=lambda t: (t[1][0], t[1][0] + t[1][1])):
+        for sub in subsets:
+            if all(g_[0] >= groups[o][0] + groups[o][1] or groups[o][0] >= g_[0] + g_[1] for o in sub):
+                sub.append(gi)
+                break
+        else:
+            subsets.append([gi])
+    proj.bwd_tables = [proj] if len(subsets) <= 1 else [_pack_groups([groups[i] for i in sub], cblocks, dev)
+                                                       for sub in subsets]
     groups, cblocks = [], []
     for p in range(P):
         first = len(cblocks)

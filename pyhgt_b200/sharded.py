@@ -336,7 +336,7 @@ class ShardedGraph:
             from .autograd import hgt_conv_autograd
             conv._check_inputs(x_local, tm)
             out = hgt_conv_autograd(conv, x_local, self.node_type, self.edge_index, self.edge_type, tm,
-                                    active=self.active_per_type)
+                                    active=self.active_per_type, kv_runs=self.kv_runs)
         else:
             out = conv(x_local, self.node_type, self.edge_index, self.edge_type, tm)
         return out.index_select(0, self.own_rows)
