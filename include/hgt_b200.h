@@ -226,8 +226,8 @@ int hgt_edge_backward(const float* q, const float* kv, const float* kvr, const f
  *   db[w_row0_g + c*cb_width + n]   += sum_m dOut_c[m, n]           (groups with has_bias)
  * dout has the layout of the forward's `out` (flat buffer addressed through the column-block table, dout_elems
  * elements).  dW / db are ACCUMULATED INTO (several groups may share W rows: the caller zero-initialises them once per
- * step); dA is written (rows no group covers are zeroed) unless accumulate_dA != 0, in which case the product is added
- * to its current content.  dA / dW / db may each be NULL to skip that product.
+ * step); dA is written (rows BETWEEN / BEFORE the groups that no group covers are zeroed; rows past the last group are the
+ * caller's) unless accumulate_dA != 0, in which case the product is added to its current content.  dA / dW / db may each be NULL to skip that product.
  * Tensor-core path (impl 0 = auto, 2 = force): tcgen05 split-bf16 x3 like the forward; takes the operands either as
  * fp32 (split here; the dout split pass also yields db) or already split by their producers (dout_hi/lo in dout's
  * layout; a_hi/a_lo [rows, K] as left by hgt_act_split in the forward) — with a pre-split dout, db is NOT computed.

@@ -96,6 +96,13 @@ class _TypedLinear(torch.autograd.Function):
         tables = getattr(ctx.table, "bwd_tables", None) or [ctx.table]
         if not ctx.use_tc:
             tables = [ctx.table]                                       # the SIMT dX uses atomics: overlap is fine
+        if need_da:
+            # hgt_typed_linear_bwd zeroes the gaps between the first table's groups; rows past its last group (other
+            # sub-tables' rows, nodes of unknown type) are zeroed here
+            g0, n0 = tables[0][1], tables[0][2]
+            end0 = int((g0["a_row0"][:n0] + g0["m"][:n0]).max()) if n0 else 0
+            if end0 < rows:
+                da[end0:].zero_()
         for ti, tab in enumerate(tables):
             g_dev, g_host, n_g, _ = tab
             c_host = tab.c_host
