@@ -246,13 +246,13 @@ def test_sharded_training_with_compaction_matches_plain_local_autograd():
     from pyhgt_b200 import sharded, synth
     from pyhgt_b200.autograd import hgt_conv_autograd
     dev = _dev()
-    g = synth.make_random(6000, 60000, 3, 4, seed=12, isolated_frac=0.1, self_loops=100)
+    g = synth.make_random(6000, 60000, 3, 2, seed=12, isolated_frac=0.1, self_loops=100)     # 6 pairs, 4 relation masks
     torch.manual_seed(4)
-    m = pyhgt_b200.HGTConv(64, 64, 3, 4, 4, 0.0, True, True).to(dev).train()
+    m = pyhgt_b200.HGTConv(64, 64, 3, 2, 4, 0.0, True, True).to(dev).train()
     old = pyhgt_b200.HGTConv.keep_att
     pyhgt_b200.HGTConv.keep_att = False
     try:
-        sh = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, g.edge_time, 3, 4, 1, 3, dev)
+        sh = sharded.ShardedGraph.build(g.node_type, g.edge_index, g.edge_type, g.edge_time, 3, 2, 1, 3, dev)
         assert sh.kv_runs is not None
         x = torch.randn(g.num_nodes, 64, generator=torch.Generator().manual_seed(5))[sh.local_global].to(dev)
         w = torch.randn(sh.n_owned, 64, generator=torch.Generator().manual_seed(6)).to(dev)
@@ -265,7 +265,7 @@ def test_sharded_training_with_compaction_matches_plain_local_autograd():
             (out * w).sum().backward()
             res.append((out.detach().clone(), xg.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}))
         from pyhgt_b200 import plan as P
-        lt = P.layer_tables(P.get_plan(sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time, 3, 4), 64, 64,
+        lt = P.layer_tables(P.get_plan(sh.node_type, sh.edge_index, sh.edge_type, sh.edge_time, 3, 2), 64, 64,
                             sh.active_per_type, sh.kv_runs)
         assert len(lt.proj_groups.bwd_tables) >= 2                 # the compacted table really has overlapping groups
     finally:
