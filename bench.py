@@ -354,7 +354,8 @@ def main_ours(args, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_to_local_numa(local_rank) if world > 1 else "not bound (single process)"
+    affinity0 = os.sched_getaffinity(0)
+    numa = None
     sampler = None
     if rank == 0:
         p = torch.cuda.get_device_properties(local_rank)
@@ -368,7 +369,7 @@ def main_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.config == "c4":
-        return main_train(args, rank, local_rank, world, dev, sampler, numa)
+        return main_train(args, rank, local_rank, world, dev, sampler, numa, affinity0)
     cfg = CONFIGS[args.config]
     D, HEADS, RTE = cfg["d"], cfg["heads"], cfg["rte"]
     g = make_graph(args.config, args.scale, args.edges_m)
@@ -526,6 +527,7 @@ def main_ours(args, rank, local_rank, world):
         # graph generation is at N = 1).
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         s_cmp = torch.cuda.current_stream()
+        numa = bind_to_local_numa(local_rank)      # the pinned staging buffers are first-touched next to the GPU's PCIe root
         if world == 1:
             host_in = [x_host.pin_memory(), g.node_type.pin_memory(), g.edge_index.pin_memory(), g.edge_type.pin_memory()]
             if RTE:
@@ -635,6 +637,10 @@ def main_ours(args, rank, local_rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, affinity0)       # the CPU arm may use every host core again
+        except OSError:
+            pass
         _, cpu, _, _, _ = run_cpu_port(args.config, steps=3, warmup=1, edges_m=args.edges_m)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -670,7 +676,7 @@ def main_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def main_train(args, rank, local_rank, world, dev, sampler, numa):
+def main_train(args, rank, local_rank, world, dev, sampler, numa, affinity0):
     """BASELINE config 4: c2 graph, 3-layer HGTConv stack (d=256, H=8, use_norm, dropout 0), forward + backward with
     gradients for every parameter (OAG/train_paper_field.py:242-252 without the optimiser step); N > 1: destination
     sharding with the differentiable halo exchange and an all-reduce of the parameter gradients."""
@@ -745,6 +751,10 @@ def main_train(args, rank, local_rank, world, dev, sampler, numa):
     peak_gb = torch.cuda.max_memory_allocated() / 1e9
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, affinity0)
+        except OSError:
+            pass
         _, cpu, _, _, _ = run_cpu_port("c4", steps=2, warmup=1)
     if rank == 0:
         value = L * E / (ms_step * 1e-3)
