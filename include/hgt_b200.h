@@ -109,10 +109,12 @@ int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t
                   int32_t width, int64_t row_base, float* out, void* stream);
 /* Same pull fused with the operand conversion of the projection GEMM: every row is written as the bf16 hi/lo split
  * (hi/lo [n_rows, width], the A operand of hgt_typed_linear_presplit) while it crosses NVLink; the fp32 copy is kept
- * only for rows owned by `self_rank` (the update epilogue's skip connection reads those).  width % 8 == 0. */
-int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row, int64_t n_rows,
-                        int32_t width, int32_t self_rank, int64_t row_base, float* out_f32, void* hi, void* lo,
-                        void* stream);
+ * only for rows owned by `self_rank` (the update epilogue's skip connection reads those).  width % 8 == 0.
+ * `order` (NULL = 0..n_rows-1): the sequence in which the rows are processed; a sequence that cycles through the owners
+ * (and starts at a different owner on every rank) keeps every NVLink source evenly loaded. */
+int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row,
+                        const int32_t* order, int64_t n_rows, int32_t width, int32_t self_rank, int64_t row_base,
+                        float* out_f32, void* hi, void* lo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Typed (per-node-type) linear layers — "per-type linear dispatch" (conv.py:73-77,96-97,103,125).

@@ -258,8 +258,9 @@ __global__ void k_halo_pull(const float* const* __restrict__ peers, const int32_
 template <int VPL>   // float4 chunks per lane and row (row = 32 * VPL float4 at most)
 __global__ void __launch_bounds__(256)
 k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restrict__ src_rank,
-                  const int32_t* __restrict__ src_row, int64_t n_rows, int vec_per_row, int self_rank, int64_t row_base,
-                  float4* __restrict__ out_f32, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+                  const int32_t* __restrict__ src_row, const int32_t* __restrict__ order, int64_t n_rows,
+                  int vec_per_row, int self_rank, int64_t row_base, float4* __restrict__ out_f32,
+                  uint2* __restrict__ hi, uint2* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -269,10 +270,18 @@ k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restr
     float4 v[RB][VPL];
     int owner[RB];
 #pragma unroll
+    int64_t rows[RB];
+#pragma unroll
     for (int b = 0; b < RB; ++b) {
-      const int64_t r = r0 + b;
+      // `order` staggers the peers: consecutive work items cycle through all owners, so every NVLink source is read by
+      // all ranks at an even rate instead of everybody draining owner 0 first
+      rows[b] = (r0 + b < n_rows) ? (order ? (int64_t)order[r0 + b] : r0 + b) : -1;
+    }
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      const int64_t r = rows[b];
       owner[b] = -1;
-      if (r < n_rows) {
+      if (r >= 0) {
         owner[b] = src_rank[r];
         const float4* src = reinterpret_cast<const float4*>(peers[owner[b]]) + (row_base + src_row[r]) * vec_per_row;
 #pragma unroll
@@ -286,8 +295,8 @@ k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restr
     }
 #pragma unroll
     for (int b = 0; b < RB; ++b) {
-      const int64_t r = r0 + b;
-      if (r >= n_rows) continue;
+      const int64_t r = rows[b];
+      if (r < 0) continue;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int c = lane + 32 * i;
@@ -470,8 +479,8 @@ extern "C" int hgt_halo_pull(uint64_t peer_ptrs_dev, const int32_t* src_rank, co
 }
 
 extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const int32_t* src_row,
-                                   int64_t n_rows, int32_t width, int32_t self_rank, int64_t row_base, float* out_f32,
-                                   void* hi, void* lo, void* stream_) {
+                                   const int32_t* order, int64_t n_rows, int32_t width, int32_t self_rank,
+                                   int64_t row_base, float* out_f32, void* hi, void* lo, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HGT_REQUIRE(width % 8 == 0, "hgt_halo_pull_split: row width %d must be a multiple of 8 floats", width);
   HGT_REQUIRE(out_f32 && hi && lo, "hgt_halo_pull_split: NULL output");
@@ -487,10 +496,10 @@ extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_ra
   auto h2 = reinterpret_cast<uint2*>(hi);
   auto l2 = reinterpret_cast<uint2*>(lo);
   const unsigned g = (unsigned)blocks, t = warps_per_block * 32;
-  if (vpr <= 32) k_halo_pull_split<1><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
-  else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
-  else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
-  else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  if (vpr <= 32) k_halo_pull_split<1><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -95,6 +95,7 @@ class ShardedGraph:
     group: object = None
     halo_mode: str = "auto"           # "nccl": one all_to_all_single per layer; "p2p": pull kernel over NVLink peer
                                       # memory; "auto": p2p on CUDA when symmetric memory works, else nccl
+    pull_order: torch.Tensor = None   # [n_local] int32: processing order of the pull kernel (peers interleaved, staggered)
     _symm: object = None
     _slot: int = 0
     kv_runs: tuple = None             # (((type, relation), ((row0, row1), ...)), ...) type-relative local rows that need K'/V'
@@ -186,6 +187,15 @@ class ShardedGraph:
         send_splits = [int(x.numel()) for x in send_lists]
         send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, **i64)
         active = torch.bincount(tkey[owned], minlength=num_types + 1).tolist()
+        # processing order of the pull kernel: the k-th row of every owner, owners taken in the order rank+1, rank+2, ...
+        # => consecutive work items cycle through all peers and no two ranks start on the same source
+        lo_owner = owner[local_global]
+        ordered = torch.argsort(lo_owner, stable=True)
+        cnt = torch.bincount(lo_owner, minlength=world)
+        start = torch.cumsum(cnt, 0) - cnt
+        k_in_owner = torch.empty_like(lo_owner)
+        k_in_owner[ordered] = torch.arange(lo_owner.numel(), device=wdev) - start[lo_owner[ordered]]
+        pull_order = torch.argsort(k_in_owner * world + (lo_owner - rank - 1) % world, stable=True).to(torch.int32)
         # "auto" (default): fused peer-memory pull on CUDA, NCCL all_to_all if symmetric memory is unavailable
         mode = halo_mode or os.environ.get("HGT_HALO", "auto")
         return ShardedGraph(rank=rank, world=world, device=device, n_owned=n_owned, n_halo=n_halo,
@@ -197,6 +207,7 @@ class ShardedGraph:
                             cat_index=order.to(torch.int32).to(device),
                             pull_rank=owner[local_global].to(torch.int32).to(device),
                             pull_row=owned_pos[local_global].to(torch.int32).to(device),
+                            pull_order=pull_order.to(device),
                             own_rows=local_of[owned].to(device), active_per_type=active, max_owned=max_owned,
                             num_types=num_types, num_relations=num_relations, group=group, halo_mode=mode,
                             kv_runs=None if kv_runs is None else tuple(sorted(kv_runs.items())))
@@ -318,8 +329,8 @@ class ShardedGraph:
             from .conv import HGTConv
             with HGTConv._stage("halo_pull_kernel"):               # bench.py: the kernel alone, without barrier / publish
                 _lib.call("hgt_halo_pull_split", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(),
-                          self.pull_row.data_ptr(), n_local, d, self.rank, slot * m, x_local.data_ptr(), hi.data_ptr(),
-                          lo.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                          self.pull_row.data_ptr(), _lib.ptr(self.pull_order), n_local, d, self.rank, slot * m,
+                          x_local.data_ptr(), hi.data_ptr(), lo.data_ptr(), torch.cuda.current_stream().cuda_stream)
             return x_local, (hi, lo)
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
                   slot * m, x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
