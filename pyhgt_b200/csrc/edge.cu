@@ -18,8 +18,6 @@
 // and per destination d*4 (Q) + d*4 (agg) + 4 (row_ptr).
 #include <cuda_bf16.h>
 
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace {
@@ -51,7 +49,6 @@ struct EdgeParams {
   float* partial;            // [n_split][2*H + d]
   int32_t* tile_counter;
   int32_t stages;            // TMA variant
-  int32_t mix;               // d_k % 4 == 2 (e.g. the OAG recipe's d_k = 50): float4 chunks + one float2 chunk per head
 };
 
 // sharded runs: destination `dst` lies past the active (owned) prefix of its node type
@@ -116,40 +113,6 @@ __device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat1
   }
 }
 
-// Mixed-width lane map (MIX): a chunk is a float4, or — one per head — a float2 whose upper two slots stay zero.
-template <int VEC, bool MIX>
-__device__ __forceinline__ void ld_chunk(float (&dst)[VEC], const float* p, bool half) {
-  if constexpr (MIX) {
-    if (half) {
-      const float2 v = *reinterpret_cast<const float2*>(p);
-      dst[0] = v.x; dst[1] = v.y; dst[2] = 0.f; dst[3] = 0.f;
-      return;
-    }
-  }
-  load_vec<VEC>(dst, p);
-}
-template <int VEC, bool MIX>
-__device__ __forceinline__ void st_chunk(float* p, const float (&src)[VEC], bool half) {
-  if constexpr (MIX) {
-    if (half) {
-      *reinterpret_cast<float2*>(p) = make_float2(src[0], src[1]);
-      return;
-    }
-  }
-  store_vec<VEC>(p, src);
-}
-template <int VEC, bool MIX>
-__device__ __forceinline__ void st_chunk_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&src)[VEC], bool half) {
-  if constexpr (MIX) {
-    if (half) {
-      const float two[2] = {src[0], src[1]};
-      store_split_bf16<2>(hi, lo, two);
-      return;
-    }
-  }
-  store_split_bf16<VEC>(hi, lo, src);
-}
-
 __device__ __forceinline__ float head_reduce(float v, int lph) {
   // lanes of one head are an aligned group of `lph` (power of two) consecutive lanes
   for (int o = lph >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -188,22 +151,9 @@ struct LaneMap {
     int o = (sub + t * lph) * VEC;
     return (head_ok && o < dk) ? base + o : -1;
   }
-  // d_k % 4 == 2 and an even number of heads: head h starts 16-byte aligned when h is even and 8 bytes off when h is
-  // odd, so its d_k floats are [float4 x n4 | float2] (even) or [float2 | float4 x n4] (odd); chunk j = sub + t*lph
-  // is the j-th float4 for j < n4 and the float2 for j == n4.
-  __device__ __forceinline__ int off_mix(int t, bool& half) const {
-    const int n4 = dk >> 2;
-    const int j = sub + t * lph;
-    half = false;
-    if (!head_ok || j > n4) return -1;
-    const bool odd = h & 1;
-    if (j < n4) return base + (odd ? 2 : 0) + 4 * j;
-    half = true;
-    return base + (odd ? 0 : 4 * n4);
-  }
 };
 
-template <int VEC, int NCH, bool MIX = false>
+template <int VEC, int NCH>
 __device__ __forceinline__ void finalize_destination(const EdgeParams& p, const LaneMap& lm, int lane, int dst,
                                                       LaneState<VEC, NCH>& st, int seg_begin, int seg_end,
                                                       bool split_piece, int pslot) {
@@ -213,9 +163,8 @@ __device__ __forceinline__ void finalize_destination(const EdgeParams& p, const 
     if (lm.head_ok && lm.sub == 0) { w[lm.h] = st.m; w[p.H + lm.h] = st.l; }
 #pragma unroll
     for (int t = 0; t < NCH; ++t) {
-      bool half = false;
-      int o = MIX ? lm.off_mix(t, half) : lm.off<VEC>(t);
-      if (o >= 0) st_chunk<VEC, MIX>(w + 2 * p.H + o, st.acc[t], half);
+      int o = lm.off<VEC>(t);
+      if (o >= 0) store_vec<VEC>(w + 2 * p.H + o, st.acc[t]);
     }
     return;
   }
@@ -223,8 +172,7 @@ __device__ __forceinline__ void finalize_destination(const EdgeParams& p, const 
   float* orow = p.agg_out + (int64_t)dst * p.d;
 #pragma unroll
   for (int t = 0; t < NCH; ++t) {
-    bool half = false;
-    int o = MIX ? lm.off_mix(t, half) : lm.off<VEC>(t);
+    int o = lm.off<VEC>(t);
     if (o >= 0) {
       float r[VEC];
 #pragma unroll
@@ -232,9 +180,8 @@ __device__ __forceinline__ void finalize_destination(const EdgeParams& p, const 
         float x = st.acc[t][v] * inv;
         r[v] = p.apply_gelu ? hgt_gelu_erf(x) : x;
       }
-      if (p.agg_out) st_chunk<VEC, MIX>(orow + o, r, half);
-      if (p.g_hi)
-        st_chunk_split<VEC, MIX>(p.g_hi + (int64_t)dst * p.d + o, p.g_lo + (int64_t)dst * p.d + o, r, half);
+      if (p.agg_out) store_vec<VEC>(orow + o, r);
+      if (p.g_hi) store_split_bf16<VEC>(p.g_hi + (int64_t)dst * p.d + o, p.g_lo + (int64_t)dst * p.d + o, r);
     }
   }
   if (p.stats_out && lm.head_ok && lm.sub == 0) {
@@ -409,7 +356,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                : "memory");
 }
 
-template <int VEC, int NCH, bool MIX = false>
+template <int VEC, int NCH>
 __global__ void __launch_bounds__(kCtaThreads, (VEC * NCH <= 4) ? 2 : 1)   // narrow rows (d_k <= 16): two CTAs per SM
 k_edge_fwd_tma(EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -430,12 +377,8 @@ k_edge_fwd_tma(EdgeParams p) {
   }
   __syncwarp();
   int offs[NCH];
-  bool half[NCH];
 #pragma unroll
-  for (int t = 0; t < NCH; ++t) {
-    half[t] = false;
-    offs[t] = MIX ? lm.off_mix(t, half[t]) : lm.off<VEC>(t);
-  }
+  for (int t = 0; t < NCH; ++t) offs[t] = lm.off<VEC>(t);
 
   uint32_t it = 0;   // rows consumed so far by this warp (slot = it % S, parity = (it / S) & 1)
 
@@ -497,7 +440,7 @@ k_edge_fwd_tma(EdgeParams p) {
         const float* qrow = p.q + (int64_t)dst * p.d;
 #pragma unroll
         for (int t = 0; t < NCH; ++t) {
-          if (offs[t] >= 0) ld_chunk<VEC, MIX>(q[t], qrow + offs[t], half[t]);
+          if (offs[t] >= 0) load_vec<VEC>(q[t], qrow + offs[t]);
           else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) q[t][v] = 0.f;
@@ -512,12 +455,12 @@ k_edge_fwd_tma(EdgeParams p) {
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
             if (offs[t] >= 0) {
-              ld_chunk<VEC, MIX>(kk[t], srow + offs[t], half[t]);
-              ld_chunk<VEC, MIX>(vv[t], srow + p.d + offs[t], half[t]);
+              load_vec<VEC>(kk[t], srow + offs[t]);
+              load_vec<VEC>(vv[t], srow + p.d + offs[t]);
               if (rte) {
                 float a[VEC], b[VEC];
-                ld_chunk<VEC, MIX>(a, srow + row_stride + offs[t], half[t]);
-                ld_chunk<VEC, MIX>(b, srow + row_stride + p.d + offs[t], half[t]);
+                load_vec<VEC>(a, srow + row_stride + offs[t]);
+                load_vec<VEC>(b, srow + row_stride + p.d + offs[t]);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { kk[t][v] += a[v]; vv[t][v] += b[v]; }
               }
@@ -544,7 +487,7 @@ k_edge_fwd_tma(EdgeParams p) {
             for (int v = 0; v < VEC; ++v) st.acc[t][v] = fmaf(pw, vv[t][v], st.acc[t][v] * scale);
         }
       }
-      finalize_destination<VEC, NCH, MIX>(p, lm, lane, dst, st, seg_begin, seg_end, split, split ? -tl.y - 1 : 0);
+      finalize_destination<VEC, NCH>(p, lm, lane, dst, st, seg_begin, seg_end, split, split ? -tl.y - 1 : 0);
       seg_begin = seg_end;
     }
   }
@@ -627,19 +570,6 @@ k_merge_partials(EdgeParams p, const int32_t* __restrict__ hubs, int n_hubs_host
   }
 }
 
-template <int NCH>
-int launch_mix(const EdgeParams& p, int grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    HGT_CHECK_CUDA(cudaFuncSetAttribute(k_edge_fwd_tma<4, NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
-  k_edge_fwd_tma<4, NCH, true><<<grid, kCtaThreads, smem, st>>>(p);
-  HGT_LAUNCH_CHECK();
-  return 0;
-}
-
 template <int VEC, int NCH>
 int launch_variant(const EdgeParams& p, int variant, int grid, size_t smem, cudaStream_t st) {
   if (variant == 1) {
@@ -647,11 +577,11 @@ int launch_variant(const EdgeParams& p, int variant, int grid, size_t smem, cuda
   } else {
     static size_t configured = 0;            // per instantiation: raise the dynamic shared-memory limit once, not per launch
     if (smem > configured) {
-      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_edge_fwd_tma<VEC, NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_edge_fwd_tma<VEC, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
       configured = smem;
     }
-    k_edge_fwd_tma<VEC, NCH, false><<<grid, kCtaThreads, smem, st>>>(p);
+    k_edge_fwd_tma<VEC, NCH><<<grid, kCtaThreads, smem, st>>>(p);
   }
   HGT_LAUNCH_CHECK();
   return 0;
@@ -720,14 +650,6 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
     if (p.DK % v == 0 && p.DK / v >= p.LPH) { vec = v; break; }
   }
   int chunks = (p.DK + vec * p.LPH - 1) / (vec * p.LPH);
-  // d_k = 4*n4 + 2 with an even number of heads (the OAG recipe: d = 400, 8 heads): 16-byte chunks plus one 8-byte chunk
-  // per head instead of 8-byte chunks throughout (TMA-ring variant only)
-  static const bool no_mix = [] { const char* e = getenv("HGT_EDGE_NO_MIX"); return e && e[0] == '1'; }();
-  p.mix = (!no_mix && vec == 2 && p.DK % 4 == 2 && n_heads % 2 == 0 && (variant == 0 || variant == 2)) ? 1 : 0;
-  if (p.mix) {
-    vec = 4;
-    chunks = (p.DK / 4 + 1 + p.LPH - 1) / p.LPH;
-  }
   int nch = 1;
   while (nch < chunks) nch <<= 1;
   HGT_REQUIRE(nch <= 8, "hgt_edge_forward: head width d_k=%d with %d heads needs %d chunks per lane (max 8)",
@@ -759,20 +681,7 @@ extern "C" int hgt_edge_forward(const float* q, const float* kv, const float* kv
   if (grid > max_ctas) grid = max_ctas;
   HGT_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), st));
   int rc;
-  if (p.mix && variant == 2) {
-    switch (nch) {
-      case 1: rc = launch_mix<1>(p, grid, smem, st); break;
-      case 2: rc = launch_mix<2>(p, grid, smem, st); break;
-      case 4: rc = launch_mix<4>(p, grid, smem, st); break;
-      default: rc = launch_mix<8>(p, grid, smem, st); break;
-    }
-  } else if (p.mix) {
-    // the ring was not usable (rows too wide): the register-gather variant keeps 8-byte chunks
-    p.mix = 0;
-    int c2 = (p.DK + 2 * p.LPH - 1) / (2 * p.LPH), n2 = 1;
-    while (n2 < c2) n2 <<= 1;
-    rc = dispatch_nch<2>(p, n2, variant, grid, smem, st);
-  } else if (vec == 4) rc = dispatch_nch<4>(p, nch, variant, grid, smem, st);
+  if (vec == 4) rc = dispatch_nch<4>(p, nch, variant, grid, smem, st);
   else if (vec == 2) rc = dispatch_nch<2>(p, nch, variant, grid, smem, st);
   else rc = dispatch_nch<1>(p, nch, variant, grid, smem, st);
   if (rc) return rc;
