@@ -225,8 +225,9 @@ class _UpdateEpilogue(torch.autograd.Function):
     def forward(ctx, o, x, skip, norm_w, norm_b, type_row0, T, perm, type_active=None):
         N, d = o.shape
         o, x = o.contiguous(), x.contiguous()
-        # with type_active (sharded training) the rows past the active prefix of a type have no output: keep them zero
-        out = (torch.zeros if type_active is not None else torch.empty)((N, d), dtype=torch.float32, device=o.device)
+        # with type_active (sharded training) the rows past the active prefix of a type have no output row: they stay
+        # unwritten (the caller selects the owned rows) and receive no gradient (hgt_update_backward skips them)
+        out = torch.empty((N, d), dtype=torch.float32, device=o.device)
         _lib.call("hgt_update_epilogue", o.data_ptr(), x.data_ptr(), type_row0.data_ptr(), T, _lib.ptr(skip),
                   _lib.ptr(norm_w), _lib.ptr(norm_b), _lib.ptr(perm), _lib.ptr(type_active), N, d, out.data_ptr(), None,
                   None, _stream())
