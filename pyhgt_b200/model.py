@@ -9,7 +9,6 @@ the one cached graph plan.  Under autograd the adapter uses the same GEMM with i
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 from . import plan as _plan
