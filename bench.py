@@ -657,7 +657,8 @@ def main_ours(args, rank, local_rank, world):
                            "parallelism": "single GPU" if world == 1 else
                                           "dst-node sharding x%d, halo source rows per step via %s" % (
                                               world, "one NCCL all_to_all_single" if shard.halo_mode == "nccl"
-                                              else "fused NVLink peer-memory pull kernel (torch symmetric memory)"),
+                                              else ("owner-push kernel over NVLink (experimental)" if shard.halo_mode == "push"
+                                                    else "fused NVLink peer-memory pull kernel (torch symmetric memory)")),
                            "linear": "tcgen05 split-bf16 (3 products, fp32 accumulate)", "edge": "TMA bulk-copy ring"},
                 "step_ms": {"stat": "median of per-step CUDA-event pairs (per-step max over ranks)",
                             "median": ms_step, "mean": sum(per_step) / len(per_step), "min": min(per_step),
@@ -788,7 +789,7 @@ def main():
     ap.add_argument("--edges-m", type=float, default=64.0, help="c5: millions of edges (sweep member)")
     ap.add_argument("--scale", type=float, default=1.0, help="graph scale (1.0 = the BASELINE size of --config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--halo", default=None, choices=["nccl", "p2p"],
+    ap.add_argument("--halo", default=None, choices=["nccl", "p2p", "push"],
                     help="multi-GPU halo exchange: one NCCL all_to_all or the fused peer-memory pull kernel (default auto)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -116,6 +116,15 @@ int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_rank, const i
                         const int32_t* order, int64_t n_rows, int32_t width, int32_t self_rank, int64_t row_base,
                         float* out_f32, void* hi, void* lo, void* stream);
 
+/* Push variant of the fused exchange (experimental): the OWNER converts its rows and stores the bf16 hi/lo split straight
+ * into the consumers' operand buffers (posted NVLink writes).  Item i: row push_src[i] of x_own [rows, width] -> row
+ * row_base + push_dst[i] of rank push_peer[i]'s hi / lo buffers (hi_ptrs_dev / lo_ptrs_dev: DEVICE arrays of world_size
+ * device pointers, peer mappings); items addressed to self_rank also write the fp32 row into x_local_f32.  The caller
+ * orders the ranks (push -> barrier -> consume; two destination areas used alternately).  width % 8 == 0. */
+int hgt_halo_push_split(const float* x_own, const int32_t* push_peer, const int32_t* push_src, const int32_t* push_dst,
+                        int64_t n_items, int32_t width, int32_t self_rank, int64_t row_base, uint64_t hi_ptrs_dev,
+                        uint64_t lo_ptrs_dev, float* x_local_f32, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Typed (per-node-type) linear layers — "per-type linear dispatch" (conv.py:73-77,96-97,103,125).
  * ---------------------------------------------------------------------------------------------- */

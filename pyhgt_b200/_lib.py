@@ -28,6 +28,7 @@ SIGNATURES = {
     "hgt_gather_rows": [_p, _p, _i64, _i32, _p, _p],
     "hgt_halo_pull": [_c.c_uint64, _p, _p, _i64, _i32, _i64, _p, _p],
     "hgt_halo_pull_split": [_c.c_uint64, _p, _p, _p, _i64, _i32, _i32, _i64, _p, _p, _p, _p],
+    "hgt_halo_push_split": [_p, _p, _p, _p, _i64, _i32, _i32, _i64, _c.c_uint64, _c.c_uint64, _p, _p],
     "hgt_fold_weights": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
                          _p, _p, _p],
     "hgt_concat_linears": [_p, _p, _i32, _i32, _i32, _p, _p, _p],

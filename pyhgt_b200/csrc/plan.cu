@@ -317,6 +317,50 @@ k_halo_pull_split(const float* const* __restrict__ peers, const int32_t* __restr
   }
 }
 
+// Push variant of the same exchange (experimental, halo_mode="push"): every OWNER converts its rows once and stores the bf16
+// hi/lo split straight into the consumers' symmetric operand buffers — posted NVLink writes instead of reads.  Work item i:
+// row push_src[i] of x_own goes to row push_dst[i] (+ row_base) of rank push_peer[i]'s buffers; the items addressed to
+// self_rank also keep the fp32 copy the skip connection needs.  The caller interleaves / staggers the peers in the item order.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+k_halo_push_split(const float4* __restrict__ x_own, const int32_t* __restrict__ push_peer,
+                  const int32_t* __restrict__ push_src, const int32_t* __restrict__ push_dst, int64_t n_items,
+                  int vec_per_row, int self_rank, int64_t row_base, uint2* const* __restrict__ hi_peers,
+                  uint2* const* __restrict__ lo_peers, float4* __restrict__ x_local_f32) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n_items; i += n_warps) {
+    const int peer = push_peer[i];
+    const float4* src = x_own + (int64_t)push_src[i] * vec_per_row;
+    const int64_t drow = (int64_t)push_dst[i];
+    uint2* hi = hi_peers[peer] + (row_base + drow) * vec_per_row;
+    uint2* lo = lo_peers[peer] + (row_base + drow) * vec_per_row;
+    float4 v[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < vec_per_row) v[k] = __ldg(src + c);
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < vec_per_row) {
+        if (peer == self_rank) x_local_f32[drow * vec_per_row + c] = v[k];
+        const float f[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __float2bfloat16_rn(f[j]);
+          l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+        }
+        hi[c] = *reinterpret_cast<uint2*>(h);
+        lo[c] = *reinterpret_cast<uint2*>(l);
+      }
+    }
+  }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -500,6 +544,32 @@ extern "C" int hgt_halo_pull_split(uint64_t peer_ptrs_dev, const int32_t* src_ra
   else if (vpr <= 64) k_halo_pull_split<2><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
   else if (vpr <= 128) k_halo_pull_split<4><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
   else k_halo_pull_split<8><<<g, t, 0, st>>>(pf, src_rank, src_row, order, n_rows, vpr, self_rank, row_base, o4, h2, l2);
+  HGT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hgt_halo_push_split(const float* x_own, const int32_t* push_peer, const int32_t* push_src,
+                                   const int32_t* push_dst, int64_t n_items, int32_t width, int32_t self_rank,
+                                   int64_t row_base, uint64_t hi_ptrs_dev, uint64_t lo_ptrs_dev, float* x_local_f32,
+                                   void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HGT_REQUIRE(width % 8 == 0 && width / 4 <= 256, "hgt_halo_push_split: row width %d must be a multiple of 8, at most 1024", width);
+  HGT_REQUIRE(x_own && push_peer && push_src && push_dst && hi_ptrs_dev && lo_ptrs_dev && x_local_f32,
+              "hgt_halo_push_split: NULL argument");
+  if (n_items == 0) return 0;
+  const int vpr = width / 4;
+  int64_t blocks = (n_items + 7) / 8;
+  const int64_t cap = (int64_t)hgt_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  auto xo = reinterpret_cast<const float4*>(x_own);
+  auto hp = reinterpret_cast<uint2* const*>(hi_ptrs_dev);
+  auto lp = reinterpret_cast<uint2* const*>(lo_ptrs_dev);
+  auto xl = reinterpret_cast<float4*>(x_local_f32);
+  const unsigned g = (unsigned)blocks;
+  if (vpr <= 32) k_halo_push_split<1><<<g, 256, 0, st>>>(xo, push_peer, push_src, push_dst, n_items, vpr, self_rank, row_base, hp, lp, xl);
+  else if (vpr <= 64) k_halo_push_split<2><<<g, 256, 0, st>>>(xo, push_peer, push_src, push_dst, n_items, vpr, self_rank, row_base, hp, lp, xl);
+  else if (vpr <= 128) k_halo_push_split<4><<<g, 256, 0, st>>>(xo, push_peer, push_src, push_dst, n_items, vpr, self_rank, row_base, hp, lp, xl);
+  else k_halo_push_split<8><<<g, 256, 0, st>>>(xo, push_peer, push_src, push_dst, n_items, vpr, self_rank, row_base, hp, lp, xl);
   HGT_LAUNCH_CHECK();
   return 0;
 }

@@ -230,7 +230,7 @@ class ShardedGraph:
         ranks in NCCL's all_to_all and others in symmetric-memory barriers.  Only the rendezvous is guarded; kernel and
         ABI errors of the pull path propagate."""
         if self.halo_mode != "auto":
-            return
+            return                                         # "nccl", "p2p" (pull) or "push" (experimental) chosen explicitly
         if not (x_own.is_cuda and self.world > 1):
             self.halo_mode = "nccl"
             return
@@ -256,7 +256,10 @@ class ShardedGraph:
         (x_local, (hi, lo) or None): on the p2p path the rows also come back as the bf16 hi/lo operand split and the fp32
         copy is valid for the owned rows only."""
         self._resolve_halo_mode(x_own)
-        if self.halo_mode == "p2p" and x_own.is_cuda and self.world > 1:
+        if self.halo_mode == "push" and x_own.is_cuda and self.world > 1 and split and x_own.shape[1] % 16 == 0 \
+                and x_own.shape[1] >= 64:
+            return self._exchange_push(x_own)
+        if self.halo_mode in ("p2p", "push") and x_own.is_cuda and self.world > 1:
             return self._exchange_p2p(x_own, split)
         res = self._exchange_nccl(x_own)
         return (res, None) if split else res
@@ -335,6 +338,59 @@ class ShardedGraph:
         _lib.call("hgt_halo_pull", hdl.buffer_ptrs_dev, self.pull_rank.data_ptr(), self.pull_row.data_ptr(), n_local, d,
                   slot * m, x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return (x_local, None) if split else x_local
+
+    # ---- push variant (experimental, opt-in with halo_mode="push") -------------------------------------------------
+    def _push_setup(self, d, device):
+        """Collective, once: turn every rank's pull plan into the owners' push plans (one all-to-all of (row, destination
+        row) pairs) and allocate the symmetric destination buffers (two areas of max_local rows for hi and for lo)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        if getattr(self, "_push", None) is not None and self._push["d"] == d:
+            return self._push
+        W, grp = self.world, (self.group if self.group is not None else dist.group.WORLD)
+        n_local = self.n_owned + self.n_halo
+        pr = self.pull_rank.long()
+        cnt_from = torch.bincount(pr, minlength=W)
+        cnt_to = torch.empty_like(cnt_from)
+        dist.all_to_all_single(cnt_to, cnt_from, group=grp)
+        order = torch.argsort(pr, stable=True)                              # my local rows grouped by their owner
+        send = torch.stack([self.pull_row.long()[order], order], 1).contiguous()
+        recv = torch.empty((int(cnt_to.sum()), 2), dtype=torch.int64, device=device)
+        dist.all_to_all_single(recv, send, output_split_sizes=cnt_to.tolist(), input_split_sizes=cnt_from.tolist(),
+                               group=grp)
+        peer = torch.repeat_interleave(torch.arange(W, device=device), cnt_to)
+        # item order: the k-th item of every consumer, consumers taken from rank+1 round the ring (same idea as pull_order)
+        start = torch.cumsum(cnt_to, 0) - cnt_to
+        k_in = torch.arange(peer.numel(), device=device) - start[peer]
+        o = torch.argsort(k_in * W + (peer - self.rank - 1) % W, stable=True)
+        mx = torch.tensor([n_local], dtype=torch.int64, device=device)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=grp)
+        max_local = int(mx.item())
+        hi = symm_mem.empty((2 * max_local, d), dtype=torch.bfloat16, device=device)
+        lo = symm_mem.empty((2 * max_local, d), dtype=torch.bfloat16, device=device)
+        h_hi, h_lo = symm_mem.rendezvous(hi, grp), symm_mem.rendezvous(lo, grp)
+        self._push = dict(d=d, peer=peer[o].to(torch.int32), src=recv[o, 0].to(torch.int32), dst=recv[o, 1].to(torch.int32),
+                          hi=hi, lo=lo, h_hi=h_hi, h_lo=h_lo, max_local=max_local, slot=0)
+        return self._push
+
+    def _exchange_push(self, x_own):
+        """Owners push: one kernel converts my owned rows and stores their bf16 hi/lo split into every consumer's operand
+        buffers (and into mine); ONE barrier, then the projection reads its operands in place."""
+        from . import _lib
+        from .conv import HGTConv
+        d = x_own.shape[1]
+        P = self._push_setup(d, x_own.device)
+        slot = P["slot"]
+        P["slot"] = slot ^ 1
+        n_local = self.n_owned + self.n_halo
+        x_local = torch.empty((n_local, d), dtype=torch.float32, device=x_own.device)   # valid for the owned rows only
+        xo = x_own.contiguous()
+        with HGTConv._stage("halo_push_kernel"):
+            _lib.call("hgt_halo_push_split", xo.data_ptr(), P["peer"].data_ptr(), P["src"].data_ptr(), P["dst"].data_ptr(),
+                      P["peer"].numel(), d, self.rank, slot * P["max_local"], P["h_hi"].buffer_ptrs_dev,
+                      P["h_lo"].buffer_ptrs_dev, x_local.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        P["h_hi"].barrier(channel=0)                  # every owner's stores have landed (and the other area is free again)
+        base = slot * P["max_local"]
+        return x_local, (P["hi"][base:base + n_local], P["lo"][base:base + n_local])
 
     def forward_train(self, conv, x_own):
         """Differentiable sharded layer (BASELINE config 4): halo exchange with a reverse all-to-all in backward, the
