@@ -354,6 +354,16 @@ uint64_t hgt_conv_args_size(void);   /* sizeof(hgt_conv_args): lets a foreign-la
 int hgt_conv_workspace_bytes(const hgt_conv_args* args, size_t* out_bytes);
 int hgt_conv_forward(const hgt_conv_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HOST helper of HGSampling (pyHGT/data.py:124-129; pyhgt_b200/sampler.py): every pointer is a HOST pointer, nothing
+ * touches the GPU.  Applies the sampled neighbours of one <target type, source type, relation> adjacency slice to the
+ * budget of the source type (flat arrays over node ids; `stamp` reproduces the reference dict's insertion order).
+ * Returns the number of budget entries added / updated, -1 if an id lies outside [0, n). */
+int64_t hgt_sampler_budget_update(const int64_t* h_ids, const int64_t* h_times, int64_t n_sampled, int64_t target_time,
+                                  int64_t no_time, int64_t max_time, int64_t n, const uint8_t* h_in_layer,
+                                  uint8_t* h_in_budget, double* h_score, int64_t* h_budget_time, int64_t* h_stamp,
+                                  int64_t* h_stamp_counter, int32_t* h_touched_layer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ _NO_TIME = np.iinfo(np.int64).min          # stands for `None` in the neighbour-
 
 class _Block:
     """One <target type, source type, relation> adjacency in CSR form, dict insertion order preserved."""
-    __slots__ = ("row_of", "ptr", "nbr", "time", "has_none")
+    __slots__ = ("row_of", "ptr", "nbr", "time", "has_none", "nbr_addr", "time_addr", "ptr_list", "row_list")
 
     def __init__(self, tesr, n_target_ids):
         keys = list(tesr.keys())
@@ -50,11 +50,15 @@ class _Block:
             self.time[pos:pos + n] = np.asarray(vals, dtype=np.int64)
             pos += n
         self.has_none = has_none
+        self.nbr_addr = self.nbr.ctypes.data               # base addresses for the native budget update
+        self.time_addr = self.time.ctypes.data
+        self.ptr_list = self.ptr.tolist()                  # plain ints: the per-node lookups stay out of numpy
+        self.row_list = self.row_of.tolist()
 
     def row(self, target_id):
-        if target_id < 0 or target_id >= self.row_of.shape[0]:
+        if target_id < 0 or target_id >= len(self.row_list):
             return -1
-        return int(self.row_of[target_id])
+        return self.row_list[target_id]
 
 
 class FrozenGraph:
@@ -100,6 +104,11 @@ class _TypeState:
         self.score = np.zeros(n, dtype=np.float64)
         self.b_time = np.zeros(n, dtype=np.int64)
         self.stamp = np.zeros(n, dtype=np.int64)
+        self._addr()
+
+    def _addr(self):
+        self.addr = (self.in_layer.shape[0], self.in_layer.ctypes.data, self.in_budget.ctypes.data,
+                     self.score.ctypes.data, self.b_time.ctypes.data, self.stamp.ctypes.data)
 
     def grow(self, n):
         if n <= self.in_layer.shape[0]:
@@ -115,6 +124,23 @@ class _TypeState:
         self.score = ext(self.score, 0.0)
         self.b_time = ext(self.b_time, 0)
         self.stamp = ext(self.stamp, 0)
+        self._addr()
+
+
+_NATIVE = [None, False]      # [function, looked up]
+
+
+def _native_update():
+    """hgt_sampler_budget_update from libhgt_b200.so (host code), or None when the library is not built: the pure numpy
+    path below gives the same result."""
+    if not _NATIVE[1]:
+        _NATIVE[1] = True
+        try:
+            from . import _lib
+            _NATIVE[0] = _lib.load().hgt_sampler_budget_update
+        except Exception:                                   # noqa: BLE001 — optional accelerator of a host-side routine
+            _NATIVE[0] = None
+    return _NATIVE[0]
 
 
 def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=None, feature_extractor=None):
@@ -126,7 +152,10 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
     states = {}                       # per type arrays
     layer_order = []                  # key order of the reference's `layer_data` defaultdict
     budget_order = []                 # key order of the reference's `budget` defaultdict
-    stamp_counter = [0]
+    stamp_counter = np.zeros(1, dtype=np.int64)
+    touched = np.zeros(1, dtype=np.int32)
+    upd = _native_update()
+    stamp_addr, touched_addr = stamp_counter.ctypes.data, touched.ctypes.data
 
     def state(_type, touch_layer=False):
         st = states.get(_type)
@@ -162,20 +191,39 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
                 row = blk.row(target_id)
                 if row < 0:
                     continue
-                a, b = int(blk.ptr[row]), int(blk.ptr[row + 1])
+                a, b = blk.ptr_list[row], blk.ptr_list[row + 1]
                 n_adl = b - a
-                if n_adl < sampled_number:                # data.py:119-122
-                    ids = blk.nbr[a:b]
-                    tms = blk.time[a:b]
+                if n_adl == 0:
+                    continue
+                st = state(source_type)
+                ids = tms = None
+                if n_adl < sampled_number:                # data.py:119-122: take the whole adjacency
+                    n_s = n_adl
+                    ids_addr, tms_addr = blk.nbr_addr + 8 * a, blk.time_addr + 8 * a
                 else:
                     # == np.random.choice(list(adl.keys()), sampled_number, replace=False): RandomState.choice draws
                     # permutation(len(a))[:size] whether `a` is the population or its size, so the stream is the same
                     pos = np.random.choice(n_adl, sampled_number, replace=False)
-                    ids = blk.nbr[a:b][pos]
-                    tms = blk.time[a:b][pos]
-                n_s = ids.shape[0]
-                if n_s == 0:
-                    continue
+                    ids = np.ascontiguousarray(blk.nbr[a:b][pos])
+                    tms = np.ascontiguousarray(blk.time[a:b][pos])
+                    n_s = ids.shape[0]
+                    ids_addr, tms_addr = ids.ctypes.data, tms.ctypes.data
+                if upd is not None:
+                    # one native call (csrc/sampler.cu) instead of a dozen small numpy operations
+                    touched[0] = 0
+                    n_arr, p_layer, p_budget, p_score, p_time, p_stamp = st.addr
+                    kept = upd(ids_addr, tms_addr, n_s, int(target_time), _NO_TIME, int(max_time), n_arr, p_layer,
+                               p_budget, p_score, p_time, p_stamp, stamp_addr, touched_addr)
+                    if kept >= 0:
+                        if touched[0]:
+                            state(source_type, touch_layer=True)
+                        if kept and source_type not in budget_seen:
+                            budget_seen.add(source_type)
+                            budget_order.append(source_type)
+                        continue
+                # numpy path: library not built, or an id past the arrays (grow them and redo this slice)
+                if ids is None:
+                    ids, tms = blk.nbr[a:b], blk.time[a:b]
                 if blk.has_none:
                     tms = np.where(tms == _NO_TIME, target_time, tms)
                 late = tms > max_time                     # data.py:126 (short-circuit `or`: layer_data[source_type] is
@@ -195,7 +243,7 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
                 new = ~st.in_budget[kid]
                 n_new = int(new.sum())
                 if n_new:
-                    st.stamp[kid[new]] = stamp_counter[0] + np.arange(n_new)
+                    st.stamp[kid[new]] = int(stamp_counter[0]) + np.arange(n_new)
                     stamp_counter[0] += n_new
                     st.in_budget[kid[new]] = True
                     st.score[kid[new]] = 0.0
