@@ -355,7 +355,7 @@ int hgt_conv_workspace_bytes(const hgt_conv_args* args, size_t* out_bytes);
 int hgt_conv_forward(const hgt_conv_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * HOST helper of HGSampling (pyHGT/data.py:124-129; pyhgt_b200/sampler.py): every pointer is a HOST pointer, nothing
+ * HOST helper of HGSampling (pyHGT/data.py:123-130; pyhgt_b200/sampler.py): every pointer is a HOST pointer, nothing
  * touches the GPU.  Applies the sampled neighbours of one <target type, source type, relation> adjacency slice to the
  * budget of the source type (flat arrays over node ids; `stamp` reproduces the reference dict's insertion order).
  * Returns the number of budget entries added / updated, -1 if an id lies outside [0, n). */

@@ -1,5 +1,5 @@
 // Host-side helper of pyhgt_b200/sampler.py (HGSampling, reference pyHGT/data.py:87-210).  Plain C++ (no device code):
-// the budget update of ONE adjacency slice — data.py:124-129, the loop over the sampled neighbours of one
+// the budget update of ONE adjacency slice — data.py:123-130, the loop over the sampled neighbours of one
 // <target type, source type, relation> block — done in one call instead of a dozen small numpy operations.
 // The random draws stay in numpy (same global RNG stream as the reference); this function is deterministic.
 #include "common.cuh"
@@ -17,10 +17,10 @@ extern "C" int64_t hgt_sampler_budget_update(const int64_t* ids, const int64_t* 
   for (int64_t i = 0; i < n_s; ++i)                         // validate before touching anything: -1 leaves the state intact
     if (ids[i] < 0 || ids[i] >= n) return -1;
   int64_t kept = 0;
-  const double w = 1.0 / (double)n_s;                       // 1. / len(sampled_ids), data.py:128
+  const double w = 1.0 / (double)n_s;                       // 1. / len(sampled_ids), data.py:129
   for (int64_t i = 0; i < n_s; ++i) {
     const int64_t tm = tms[i] == no_time ? target_time : tms[i];
-    if (tm > max_time) continue;                            // data.py:126, first operand of the `or`
+    if (tm > max_time) continue;                            // data.py:127, first operand of the `or`
     *touched_layer = 1;
     const int64_t id = ids[i];
     if (in_layer[id]) continue;                             // second operand

@@ -20,7 +20,7 @@ from collections import defaultdict
 
 import numpy as np
 
-_NO_TIME = np.iinfo(np.int64).min          # stands for `None` in the neighbour-time arrays (data.py:121-123)
+_NO_TIME = np.iinfo(np.int64).min          # stands for `None` in the neighbour-time arrays (data.py:125-126)
 
 
 class _Block:
@@ -226,7 +226,7 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
                     ids, tms = blk.nbr[a:b], blk.time[a:b]
                 if blk.has_none:
                     tms = np.where(tms == _NO_TIME, target_time, tms)
-                late = tms > max_time                     # data.py:126 (short-circuit `or`: layer_data[source_type] is
+                late = tms > max_time                     # data.py:127 (short-circuit `or`: layer_data[source_type] is
                 if late.all():                            # only touched when some candidate passes the time test)
                     continue
                 st = state(source_type, touch_layer=True)
@@ -247,10 +247,10 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
                     stamp_counter[0] += n_new
                     st.in_budget[kid[new]] = True
                     st.score[kid[new]] = 0.0
-                st.score[kid] += 1.0 / n_s                # data.py:128 (ids are unique inside one adjacency)
-                st.b_time[kid] = ktm                      # data.py:129
+                st.score[kid] += 1.0 / n_s                # data.py:129 (ids are unique inside one adjacency)
+                st.b_time[kid] = ktm                      # data.py:130
 
-    # first adding the sampled nodes then updating budget (data.py:134-140)
+    # first adding the sampled nodes then updating budget (data.py:135-141)
     for _type in inp:
         for _id, _time in inp[_type]:
             add_layer(_type, _id, _time)

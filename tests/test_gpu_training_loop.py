@@ -68,7 +68,7 @@ def test_sampled_minibatch_training_reduces_the_loss():
             nf, nt, etime, ei, et, node_dict, _ = hdata.to_torch(feature, times, edge_list, g, device=dev, prebuild_plan=True)
             out = gnn(nf, nt, etime, ei, et)
             p0 = node_dict["paper"][0]
-            logits = head(out[p0:p0 + len(batch)])                    # the seed papers are the first papers (data.py:134-136)
+            logits = head(out[p0:p0 + len(batch)])                    # the seed papers are the first papers (data.py:135-137)
             loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(venue_of[batch]).to(dev))
             opt.zero_grad()
             loss.backward()
