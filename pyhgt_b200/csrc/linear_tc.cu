@@ -318,10 +318,64 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t t_row, int n_cols, int
   }
 }
 
+// Same tile, software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i goes through the staging buffer
+// and out to global memory (two named register buffers), and the staging buffer is swizzled so that neither side has
+// bank conflicts.  Measured at C2 together with the .cta-scope pair barriers below: projection 3.90 -> 3.81 ms
+// (profiles/r02_gemm_epilogue_ab.md); the kernel stays bound by the shared-memory port (MMA operand fetch + TMA fill +
+// this transpose), see DESIGN.md section 9.
+__device__ __forceinline__ void tc_epi_chunk(const uint32_t (&r)[16], int c0, float* stg, const float* s_bias,
+                                             float* out_tile, int64_t ld, int64_t rows_left, int lane) {
+  // staging rows of 64 bytes, the 16-byte piece j of row r kept at position j ^ ((r >> 1) & 3): the row-per-lane writes
+  // and the 4-lanes-per-row reads both touch every bank once per quarter warp (no conflicts, 4 wavefronts per access)
+  const int sub = lane & 3, rsel = lane >> 2;
+  const int wsw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) =
+        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + sub * 4);
+  const int rsw = (sub ^ ((rsel >> 1) & 3)) << 2;                     // (8k + rsel) >> 1 & 3 == rsel >> 1 & 3
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(stg + (8 * k + rsel) * 16 + rsw);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = 8 * k + rsel;
+    if (rr < rows_left) {
+      float4 w = v[k];
+      w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+      *reinterpret_cast<float4*>(out_tile + (int64_t)rr * ld + c0 + sub * 4) = w;
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue_tile_pf(uint32_t t_row, int n_cols, int chunk0, float* stg,
+                                                    const float* s_bias, float* out_tile, int64_t ld,
+                                                    int64_t rows_left, int lane) {
+  uint32_t ra[16], rb[16];
+  int c0 = 16 * chunk0;
+  if (c0 >= n_cols) return;
+  tmem_ld16(t_row + (uint32_t)c0, ra);
+  for (; c0 < n_cols; c0 += 64) {
+    const bool has_b = c0 + 32 < n_cols;
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");       // ra has landed
+    if (has_b) tmem_ld16(t_row + (uint32_t)(c0 + 32), rb);
+    tc_epi_chunk(ra, c0, stg, s_bias, out_tile, ld, rows_left, lane);
+    if (!has_b) break;
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");       // rb has landed
+    if (c0 + 64 < n_cols) tmem_ld16(t_row + (uint32_t)(c0 + 64), ra);
+    tc_epi_chunk(rb, c0 + 32, stg, s_bias, out_tile, ld, rows_left, lane);
+  }
+}
+
 struct Tc2Sched {
   int32_t first_unit[kMaxGroups + 1];
   int32_t n_tiles_n;
+  int32_t epi;                                   // bit 0: pipelined epilogue; bit 1: .cta-scope pair barriers (default 3)
 };
+static int tc2_epi() { static int v = [] { const char* e = getenv("HGT_TC_EPI"); return e ? atoi(e) : 3; }(); return v; }
 
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -497,8 +551,12 @@ k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_wait(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t m0 = (un.m_first + mt) * TC_BM + lg * 32;
-        tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, stg, s_bias,
-                         out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        if (sc.epi & 1)
+          tc_epilogue_tile_pf(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, stg, s_bias,
+                              out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        else
+          tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, stg, s_bias,
+                           out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&t_empty[buf])) : "memory");
@@ -559,27 +617,55 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       ::"r"(bar), "h"((uint16_t)3)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-      "}"
-      ::"r"(bar), "r"(cta)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  // acquire at cluster scope: the barrier may have been completed by the peer CTA's arrivals
-  uint32_t ok = 0;
-  while (!ok) {
+// Barrier traffic between the two CTAs of a pair carries no generic-proxy data: operands arrive through TMA
+// (complete_tx), accumulators are handed over with tcgen05.commit / tcgen05.fence.  The arrive / wait therefore use the
+// default .cta-scope forms.  (The .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR, which made every
+// epilogue warp wait for its global stores to be acknowledged before it could hand the accumulator back, and the
+// .acquire.cluster wait adds an L1 invalidate per wait: profiles/r02_gemm_tc3_c2_epi1_ncu_raw.csv, stall_membar = 20 %
+// of the warp samples.)
+// `strong` keeps the old forms for A/B runs (HGT_TC_EPI bit 1 clear).
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta, bool strong) {
+  if (strong)
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
         "}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        ::"r"(bar), "r"(cta)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, bool strong) {
+  uint32_t ok = 0;
+  if (strong) {
+    while (!ok) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+  } else {
+    while (!ok) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
   }
 }
 
@@ -618,6 +704,7 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   const int pair_id = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
   const int total_units = sc.first_unit[n_groups];
+  const bool strong = !(sc.epi & 2);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -681,7 +768,7 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       for (int u = pair_id; u < total_units; u += n_pairs, ++unit_it) {
         Unit un;
         decode(u, un);
-        mbar_wait_cluster(s_u32(w_empty), (unit_it & 1u) ^ 1u);
+        mbar_wait_cluster(s_u32(w_empty), (unit_it & 1u) ^ 1u, strong);
         if (leader) mbar_expect_tx(s_u32(w_full), 2u * (uint32_t)k_blocks * 2 * b_bytes);
         const int w_row = un.w_row + (int)cta * BNH;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -692,7 +779,7 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const int a_row = un.a_row0 + (int)((un.pm_first + pm) * BMP) + (int)cta * TC_BM;
           for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
             const int s = a_it % stages;
-            mbar_wait_cluster(s_u32(&a_empty[s]), ((a_it / stages) & 1u) ^ 1u);
+            mbar_wait_cluster(s_u32(&a_empty[s]), ((a_it / stages) & 1u) ^ 1u, strong);
             const uint32_t bar = s_u32(&a_full[s]);
             if (leader) mbar_expect_tx(bar, 2u * a_bytes);
             tma_load_2d_2sm(s_u32(a_smem + (size_t)s * a_bytes), (j & 1) ? &map_a_lo : &map_a_hi, (j >> 1) * TC_BK,
@@ -710,16 +797,16 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       for (int u = pair_id; u < total_units; u += n_pairs, ++unit_it) {
         Unit un;
         decode(u, un);
-        mbar_wait_cluster(s_u32(w_full), unit_it & 1u);
+        mbar_wait_cluster(s_u32(w_full), unit_it & 1u, strong);
         for (int pm = 0; pm < un.n_pm; ++pm, ++acc_it) {
           const uint32_t buf = acc_it & 1u;
-          mbar_wait_cluster(s_u32(&t_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u);
+          mbar_wait_cluster(s_u32(&t_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u, strong);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_d = tmem_base + buf * (uint32_t)BNP;
           for (int j = 0; j < 2 * k_blocks; ++j, ++a_it) {
             const int s = a_it % stages;
             const int kb = j >> 1;
-            mbar_wait_cluster(s_u32(&a_full[s]), (a_it / stages) & 1u);
+            mbar_wait_cluster(s_u32(&a_full[s]), (a_it / stages) & 1u, strong);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t d_a = make_sw128_desc(s_u32(a_smem + (size_t)s * a_bytes));
             const uint64_t d_whi = make_sw128_desc(s_u32(w_smem + (size_t)(2 * kb) * b_bytes));
@@ -760,14 +847,18 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int pm = 0; pm < un.n_pm; ++pm, ++acc_it) {
         const uint32_t buf = acc_it & 1u;
-        mbar_wait_cluster(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
+        mbar_wait_cluster(s_u32(&t_full[buf]), (acc_it >> 1) & 1u, strong);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t m0 = (un.pm_first + pm) * BMP + (int64_t)cta * TC_BM + lg * 32;
-        tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, stg, s_bias,
-                         out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        if (sc.epi & 1)
+          tc_epilogue_tile_pf(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, stg, s_bias,
+                              out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        else
+          tc_epilogue_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, stg, s_bias,
+                           out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cta(s_u32(&t_empty[buf]), 0);      // the leader's barrier collects both CTAs
+        if (lane == 0) mbar_arrive_cta(s_u32(&t_empty[buf]), 0, strong);      // the leader's barrier collects both CTAs
       }
     }
   }
@@ -937,6 +1028,7 @@ static int tc_run(const float* A, int64_t lda, const __nv_bfloat16* a_hi_in, con
       Tc2Sched sc;
       const int mch = tc2_mch();
       sc.n_tiles_n = cb_width / 256;
+      sc.epi = tc2_epi();
       int64_t units = 0;
       for (int g = 0; g < n_groups; ++g) {
         sc.first_unit[g] = (int32_t)units;
@@ -950,9 +1042,9 @@ static int tc_run(const float* A, int64_t lda, const __nv_bfloat16* a_hi_in, con
       if ((rc = make_map(&m_w_lo, w_lo, w_rows, Kp, 128))) return rc;
       size_t smem = 1024 + w_region + (size_t)stages * a_stage + (2 * stages + 6) * 8 + 16 + 256 * 4 + 64 +
                     TC2_STAGE_BYTES;
-      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_typed_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int pairs = hgt_sm_count() / 2;
       if (pairs > units) pairs = (int)units;
+      HGT_CHECK_CUDA(cudaFuncSetAttribute(k_typed_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_typed_linear_tc3<<<2 * pairs, TC2_THREADS, smem, st>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, bias, Kp, cb_width,
                                                                stages, groups, n_groups, cblocks, out, sc, mch);
       HGT_LAUNCH_CHECK();
@@ -981,6 +1073,7 @@ static int tc_run(const float* A, int64_t lda, const __nv_bfloat16* a_hi_in, con
         Tc2Sched sc;
         const int mch = tc2_mch();
         sc.n_tiles_n = cb_width / bn;
+        sc.epi = tc2_epi();
         int64_t units = 0;
         for (int g = 0; g < n_groups; ++g) {
           sc.first_unit[g] = (int32_t)units;
