@@ -370,6 +370,60 @@ __device__ __forceinline__ void tc_epilogue_tile_pf(uint32_t t_row, int n_cols, 
   }
 }
 
+// Direct drain (HGT_TC_EPI bit 2): tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of an accumulator
+// row (the m16n8 fragment layout: registers {0,1} = row lane/4, columns 2*(lane%4)+{0,1}; {2,3} = row lane/4 + 8; the next
+// four registers the next 8 columns), so the tile goes from registers to global memory as full 32-byte sectors with no
+// trip through shared memory — the transpose is the third client of the shared-memory port next to the MMA operand
+// fetch and the TMA fill (profiles/r02_gemm_epilogue_ab.md).  A warp covers its 32 TMEM lanes with two 16-lane loads.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+__device__ __forceinline__ void tc_epi_direct_store(const uint32_t (&v)[8], int row0, int c0, const float* s_bias,
+                                                    float* out_tile, int64_t ld, int64_t rows_left, int lane) {
+  const int q = lane & 3, r0 = row0 + (lane >> 2);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int col = c0 + 8 * i + 2 * q;
+    const float2 b = *reinterpret_cast<const float2*>(s_bias + col);
+    if (r0 < rows_left)
+      *reinterpret_cast<float2*>(out_tile + (int64_t)r0 * ld + col) =
+          make_float2(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y);
+    if (r0 + 8 < rows_left)
+      *reinterpret_cast<float2*>(out_tile + (int64_t)(r0 + 8) * ld + col) =
+          make_float2(__uint_as_float(v[4 * i + 2]) + b.x, __uint_as_float(v[4 * i + 3]) + b.y);
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue_tile_direct(uint32_t t_row, int n_cols, int chunk0, const float* s_bias,
+                                                        float* out_tile, int64_t ld, int64_t rows_left, int lane) {
+  uint32_t a0[8], a1[8], b0[8], b1[8];                       // (rows 0-15, rows 16-31) of two chunks in flight
+  int c0 = 16 * chunk0;
+  if (c0 >= n_cols) return;
+  tmem_ld_16x256b_x2(t_row + (uint32_t)c0, a0);
+  tmem_ld_16x256b_x2(t_row + (16u << 16) + (uint32_t)c0, a1);
+  for (; c0 < n_cols; c0 += 64) {
+    const bool has_b = c0 + 32 < n_cols;
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (has_b) {
+      tmem_ld_16x256b_x2(t_row + (uint32_t)(c0 + 32), b0);
+      tmem_ld_16x256b_x2(t_row + (16u << 16) + (uint32_t)(c0 + 32), b1);
+    }
+    tc_epi_direct_store(a0, 0, c0, s_bias, out_tile, ld, rows_left, lane);
+    tc_epi_direct_store(a1, 16, c0, s_bias, out_tile, ld, rows_left, lane);
+    if (!has_b) break;
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c0 + 64 < n_cols) {
+      tmem_ld_16x256b_x2(t_row + (uint32_t)(c0 + 64), a0);
+      tmem_ld_16x256b_x2(t_row + (16u << 16) + (uint32_t)(c0 + 64), a1);
+    }
+    tc_epi_direct_store(b0, 0, c0 + 32, s_bias, out_tile, ld, rows_left, lane);
+    tc_epi_direct_store(b1, 16, c0 + 32, s_bias, out_tile, ld, rows_left, lane);
+  }
+}
+
 struct Tc2Sched {
   int32_t first_unit[kMaxGroups + 1];
   int32_t n_tiles_n;
@@ -551,7 +605,10 @@ k_typed_linear_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_wait(s_u32(&t_full[buf]), (acc_it >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t m0 = (un.m_first + mt) * TC_BM + lg * 32;
-        if (sc.epi & 1)
+        if (sc.epi & 4)
+          tc_epilogue_tile_direct(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, s_bias,
+                                  out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        else if (sc.epi & 1)
           tc_epilogue_tile_pf(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BN, BN, e >> 2, stg, s_bias,
                               out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         else
@@ -850,7 +907,10 @@ k_typed_linear_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_wait_cluster(s_u32(&t_full[buf]), (acc_it >> 1) & 1u, strong);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t m0 = (un.pm_first + pm) * BMP + (int64_t)cta * TC_BM + lg * 32;
-        if (sc.epi & 1)
+        if (sc.epi & 4)
+          tc_epilogue_tile_direct(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, s_bias,
+                                  out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
+        else if (sc.epi & 1)
           tc_epilogue_tile_pf(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)BNP, BNP, e >> 2, stg, s_bias,
                               out + un.out_off + m0 * un.ld + un.n0, un.ld, un.m_rows - m0, lane);
         else
