@@ -321,8 +321,7 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t t_row, int n_cols, int
 // Same tile, software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i goes through the staging buffer
 // and out to global memory (two named register buffers), and the staging buffer is swizzled so that neither side has
 // bank conflicts.  Measured at C2 together with the .cta-scope pair barriers below: projection 3.90 -> 3.81 ms
-// (profiles/r02_gemm_epilogue_ab.md); the kernel stays bound by the shared-memory port (MMA operand fetch + TMA fill +
-// this transpose), see DESIGN.md section 9.
+// (profiles/r02_gemm_epilogue_ab.md); see DESIGN.md section 9 for what was ruled out as the limiter.
 __device__ __forceinline__ void tc_epi_chunk(const uint32_t (&r)[16], int c0, float* stg, const float* s_bias,
                                              float* out_tile, int64_t ld, int64_t rows_left, int lane) {
   // staging rows of 64 bytes, the 16-byte piece j of row r kept at position j ^ ((r >> 1) & 3): the row-per-lane writes
@@ -370,11 +369,13 @@ __device__ __forceinline__ void tc_epilogue_tile_pf(uint32_t t_row, int n_cols, 
   }
 }
 
-// Direct drain (HGT_TC_EPI bit 2): tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of an accumulator
-// row (the m16n8 fragment layout: registers {0,1} = row lane/4, columns 2*(lane%4)+{0,1}; {2,3} = row lane/4 + 8; the next
-// four registers the next 8 columns), so the tile goes from registers to global memory as full 32-byte sectors with no
-// trip through shared memory — the transpose is the third client of the shared-memory port next to the MMA operand
-// fetch and the TMA fill (profiles/r02_gemm_epilogue_ab.md).  A warp covers its 32 TMEM lanes with two 16-lane loads.
+// Direct drain (HGT_TC_EPI bit 2, opt-in): tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of an
+// accumulator row (the m16n8 fragment layout: registers {0,1} = row lane/4, columns 2*(lane%4)+{0,1}; {2,3} = row
+// lane/4 + 8; the next four registers the next 8 columns), so the tile goes from registers to global memory as full
+// 32-byte sectors with no trip through shared memory.  A warp covers its 32 TMEM lanes with two 16-lane loads.
+// Parity-green on the whole GPU suite and the SAME speed as the staged drain at C2 (projection 3.778 vs 3.788 ms,
+// profiles/r02_gemm_epilogue_ab.md) — so the transpose's share of the shared-memory port is not what holds the kernel;
+// kept as an option because it needs no staging buffer.
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -427,7 +428,7 @@ __device__ __forceinline__ void tc_epilogue_tile_direct(uint32_t t_row, int n_co
 struct Tc2Sched {
   int32_t first_unit[kMaxGroups + 1];
   int32_t n_tiles_n;
-  int32_t epi;                                   // bit 0: pipelined epilogue; bit 1: .cta-scope pair barriers (default 3)
+  int32_t epi;                                   // bit 0: pipelined epilogue; bit 1: .cta-scope pair barriers; bit 2: direct drain (default 3)
 };
 static int tc2_epi() { static int v = [] { const char* e = getenv("HGT_TC_EPI"); return e ? atoi(e) : 3; }(); return v; }
 
