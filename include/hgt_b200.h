@@ -364,6 +364,27 @@ int64_t hgt_sampler_budget_update(const int64_t* h_ids, const int64_t* h_times, 
                                   uint8_t* h_in_budget, double* h_score, int64_t* h_budget_time, int64_t* h_stamp,
                                   int64_t* h_stamp_counter, int32_t* h_touched_layer);
 
+/* One <target type, source type, relation> adjacency of the frozen graph in CSR form (host arrays; rows in the
+ * reference dict's insertion order) and the layer_data / budget of one node type as flat arrays over node ids. */
+typedef struct {
+  const int64_t* row_of; int64_t n_row_of;   /* target id -> CSR row, -1 = no adjacency */
+  const int64_t* ptr; const int64_t* nbr; const int64_t* time;
+  int32_t src_state;                         /* index of the source type's hgt_sampler_state */
+  int32_t skip;                              /* 1 for the 'self' relation (data.py:116) */
+} hgt_sampler_block;
+typedef struct {
+  int64_t n;
+  uint8_t* in_layer; uint8_t* in_budget; double* score; int64_t* b_time; int64_t* stamp;
+  int64_t* log; int64_t log_len;             /* ids in budget-insertion order (capacity n) */
+  int64_t layer_seq; int64_t budget_seq;     /* first-touch numbers of layer_data[type] / budget[type], -1 = untouched */
+} hgt_sampler_state;
+/* add_budget (pyHGT/data.py:108-130) for a batch of target nodes of one type, target-major, blocks in dict order; the
+ * uniform draws are made by the caller (numpy's global RNG, same order) and passed as positions.  0 = ok. */
+int64_t hgt_sampler_add_budget(const int64_t* h_target_ids, const int64_t* h_target_times, int64_t n_targets,
+                               const hgt_sampler_block* h_blocks, int32_t n_blocks, hgt_sampler_state* h_states,
+                               int32_t n_states, int64_t sampled_number, const int64_t* h_draw_off,
+                               const int64_t* h_draw_pos, int64_t no_time, int64_t max_time, int64_t* h_counters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,8 @@ def load():
     lib.hgt_conv_args_size.argtypes = []
     lib.hgt_sampler_budget_update.restype = _c.c_int64       # host helper of sampler.py: returns a count, not a status
     lib.hgt_sampler_budget_update.argtypes = [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]
+    lib.hgt_sampler_add_budget.restype = _c.c_int64
+    lib.hgt_sampler_add_budget.argtypes = [_p, _p, _i64, _p, _c.c_int32, _p, _c.c_int32, _i64, _p, _p, _i64, _i64, _p]
     _lib = lib
     return lib
 

@@ -11,16 +11,33 @@ and ``to_torch`` then emits the same tensors.  What changes is the data structur
     insertion stamp reproduces ``list(budget.keys())`` order, including pop-and-re-insert;
   * the final "reconstruct the sampled adjacency" triple loop (data.py:190-209: every sampled target x every neighbour,
     membership tests in Python dicts) becomes one gather + mask per <target type, source type, relation>.
+  * ``add_budget`` (data.py:108-130) runs for a whole batch of newly sampled nodes in one native call
+    (``hgt_sampler_add_budget``, csrc/sampler.cu, host code): the uniform draws do not depend on the budget, so numpy
+    makes them first, in the reference's target-major order, and the native loop applies them; the key order of the
+    budget dict comes from an append-only insertion log instead of a sort.  ``_sample_slices`` is the same process with
+    one update per adjacency slice (native or numpy) — the fallback when the library is not built.
 
 The sampled ``edge_list`` values are ``[E_block, 2]`` int64 arrays of ``[target_ser, source_ser]`` rows (the reference
 builds Python lists of pairs with the same content and order); ``pyhgt_b200.data.to_torch`` and the reference's
 ``to_torch`` accept both.
 """
+import ctypes as _c
 from collections import defaultdict
 
 import numpy as np
 
 _NO_TIME = np.iinfo(np.int64).min          # stands for `None` in the neighbour-time arrays (data.py:125-126)
+
+
+class _CBlock(_c.Structure):                 # hgt_sampler_block (include/hgt_b200.h)
+    _fields_ = [("row_of", _c.c_void_p), ("n_row_of", _c.c_int64), ("ptr", _c.c_void_p), ("nbr", _c.c_void_p),
+                ("time", _c.c_void_p), ("src_state", _c.c_int32), ("skip", _c.c_int32)]
+
+
+class _CState(_c.Structure):                 # hgt_sampler_state
+    _fields_ = [("n", _c.c_int64), ("in_layer", _c.c_void_p), ("in_budget", _c.c_void_p), ("score", _c.c_void_p),
+                ("b_time", _c.c_void_p), ("stamp", _c.c_void_p), ("log", _c.c_void_p), ("log_len", _c.c_int64),
+                ("layer_seq", _c.c_int64), ("budget_seq", _c.c_int64)]
 
 
 class _Block:
@@ -87,9 +104,32 @@ class FrozenGraph:
                 for r, tesr in d2.items():
                     self.blocks[t_t][s_t][r] = _Block(tesr, self.n_ids.get(t_t, 0))
 
+        self.types = []                                   # every type that occurs, targets first (index = native state slot)
+        for t_t, d1 in graph.edge_list.items():
+            for ty in [t_t] + list(d1.keys()):
+                if ty not in self.types:
+                    self.types.append(ty)
+        self.type_idx = {ty: i for i, ty in enumerate(self.types)}
+        self._cblocks = {}
+
     def ensure_ids(self, _type, max_id):
         if max_id + 1 > self.n_ids.get(_type, 0):
             self.n_ids[_type] = max_id + 1
+
+    def native_blocks(self, target_type):
+        """(ctypes array of hgt_sampler_block, [(source type index, _Block, skip)], ...) of one target type, blocks in the
+        reference's dict order (data.py:113,115); None when the type has no in-edges."""
+        ent = self._cblocks.get(target_type)
+        if ent is None and target_type in self.blocks:
+            lst = [(self.type_idx[s_t], blk, 1 if r == 'self' else 0)
+                   for s_t, tes in self.blocks[target_type].items() for r, blk in tes.items()]
+            arr = (_CBlock * max(len(lst), 1))()
+            for i, (si, blk, skip) in enumerate(lst):
+                arr[i].row_of, arr[i].n_row_of = blk.row_of.ctypes.data, blk.row_of.shape[0]
+                arr[i].ptr, arr[i].nbr, arr[i].time = blk.ptr.ctypes.data, blk.nbr_addr, blk.time_addr
+                arr[i].src_state, arr[i].skip = si, skip
+            ent = self._cblocks[target_type] = (arr, lst)
+        return ent
 
 
 class _TypeState:
@@ -104,6 +144,7 @@ class _TypeState:
         self.score = np.zeros(n, dtype=np.float64)
         self.b_time = np.zeros(n, dtype=np.int64)
         self.stamp = np.zeros(n, dtype=np.int64)
+        self.log = np.empty(n, dtype=np.int64)             # ids in budget-insertion order (written by the native path)
         self._addr()
 
     def _addr(self):
@@ -124,10 +165,29 @@ class _TypeState:
         self.score = ext(self.score, 0.0)
         self.b_time = ext(self.b_time, 0)
         self.stamp = ext(self.stamp, 0)
+        self.log = ext(self.log, 0)
         self._addr()
+
+    def to_c(self, c):
+        c.n = self.in_layer.shape[0]
+        c.in_layer, c.in_budget, c.score = self.in_layer.ctypes.data, self.in_budget.ctypes.data, self.score.ctypes.data
+        c.b_time, c.stamp, c.log = self.b_time.ctypes.data, self.stamp.ctypes.data, self.log.ctypes.data
 
 
 _NATIVE = [None, False]      # [function, looked up]
+_NATIVE_BATCH = [None, False]
+
+
+def _native_batch():
+    """hgt_sampler_add_budget (whole add_budget for a batch of targets) or None when the library is not built."""
+    if not _NATIVE_BATCH[1]:
+        _NATIVE_BATCH[1] = True
+        try:
+            from . import _lib
+            _NATIVE_BATCH[0] = _lib.load().hgt_sampler_add_budget
+        except Exception:                                   # noqa: BLE001 — optional accelerator of a host-side routine
+            _NATIVE_BATCH[0] = None
+    return _NATIVE_BATCH[0]
 
 
 def _native_update():
@@ -147,6 +207,127 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
     """Drop-in for pyHGT/data.py:87 ``sample_subgraph``.  `graph` is a reference ``Graph`` or a ``FrozenGraph`` of it
     (freeze once, sample many batches).  Consumes numpy's global RNG exactly like the reference."""
     fg = graph if isinstance(graph, FrozenGraph) else FrozenGraph(graph)
+    if _native_batch() is not None and all(t in fg.type_idx for t in inp):
+        return _sample_batched(fg, time_range, sampled_depth, sampled_number, inp, feature_extractor)
+    return _sample_slices(fg, time_range, sampled_depth, sampled_number, inp, feature_extractor)
+
+
+def _sample_batched(fg, time_range, sampled_depth, sampled_number, inp, feature_extractor):
+    """One native call per <sampling layer, node type>: the whole add_budget of the batch of newly sampled nodes runs in
+    csrc/sampler.cu; numpy only makes the random draws (same order as the reference, see hgt_sampler_add_budget)."""
+    nat = _native_batch()
+    max_time = int(np.max(list(time_range.keys())))
+    T = len(fg.types)
+    cst = (_CState * max(T, 1))()
+    for i in range(T):
+        cst[i].layer_seq = cst[i].budget_seq = -1
+    sts = [None] * T
+    counters = np.zeros(3, dtype=np.int64)                # budget stamp, layer_data first touch, budget first touch
+
+    def state(i):
+        st = sts[i]
+        if st is None:
+            st = sts[i] = _TypeState(fg.n_ids.get(fg.types[i], 0))
+            st.to_c(cst[i])
+        return st
+
+    def type_index(_type):
+        i = fg.type_idx.get(_type)
+        if i is None:
+            raise KeyError("sample_subgraph: node type %r does not occur in graph.edge_list" % (_type,))
+        return i
+
+    def touch_layer(i):
+        if cst[i].layer_seq < 0:
+            cst[i].layer_seq = int(counters[1])
+            counters[1] += 1
+
+    def add_layer(i, _id, _time):
+        st = state(i)
+        touch_layer(i)
+        if _id >= st.in_layer.shape[0]:
+            fg.ensure_ids(fg.types[i], _id)
+            st.grow(fg.n_ids[fg.types[i]])
+            st.to_c(cst[i])
+        st.ser[_id] = len(st.layer_ids)                   # re-adding an id overwrites [ser, time] (dict semantics)
+        if not st.in_layer[_id]:
+            st.layer_ids.append(_id)
+        st.in_layer[_id] = True
+        st.layer_time[_id] = _time
+
+    def add_budget(i, ids, tms):
+        ent = fg.native_blocks(fg.types[i])
+        if ent is None or ids.shape[0] == 0:
+            return
+        arr, lst = ent
+        nb = len(lst)
+        need = []
+        for b, (si, blk, skip) in enumerate(lst):
+            state(si)
+            if skip:
+                continue
+            inside = (ids >= 0) & (ids < blk.row_of.shape[0])
+            rows = np.where(inside, blk.row_of[np.where(inside, ids, 0)], -1)
+            cnt = np.where(rows >= 0, blk.ptr[rows + 1] - blk.ptr[rows], 0)
+            for t in np.nonzero((cnt >= sampled_number) & (cnt > 0))[0]:
+                need.append((int(t), b, int(cnt[t])))
+        off_ptr = pos_ptr = None
+        if need:
+            need.sort()                                   # the reference draws target after target, block after block
+            draw_off = np.full(ids.shape[0] * nb, -1, dtype=np.int64)
+            chunks = []
+            for k, (t, b, n_adl) in enumerate(need):
+                # == np.random.choice(list(adl.keys()), sampled_number, replace=False): RandomState.choice draws
+                # permutation(len(a))[:size] whether `a` is the population or its size, so the stream is the same
+                chunks.append(np.random.choice(n_adl, sampled_number, replace=False))
+                draw_off[t * nb + b] = k * sampled_number
+            draw_pos = np.ascontiguousarray(np.concatenate(chunks), dtype=np.int64)
+            off_ptr, pos_ptr = draw_off.ctypes.data, draw_pos.ctypes.data
+        rc = nat(ids.ctypes.data, tms.ctypes.data, ids.shape[0], arr, nb, cst, T, sampled_number, off_ptr, pos_ptr,
+                 _NO_TIME, max_time, counters.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("hgt_sampler_add_budget failed (%d): neighbour id outside the frozen graph's id range" % rc)
+
+    # first adding the sampled nodes then updating budget (data.py:135-141)
+    for _type in inp:
+        i = type_index(_type)
+        for _id, _time in inp[_type]:
+            add_layer(i, int(_id), int(_time))
+    for _type in inp:
+        arr_in = np.asarray(inp[_type], dtype=np.int64).reshape(-1, 2)
+        add_budget(type_index(_type), np.ascontiguousarray(arr_in[:, 0]), np.ascontiguousarray(arr_in[:, 1]))
+
+    for _layer in range(sampled_depth):                   # data.py:147
+        order = sorted((i for i in range(T) if cst[i].budget_seq >= 0), key=lambda i: cst[i].budget_seq)
+        for i in order:                                   # sts = list(budget.keys())
+            st = sts[i]
+            log = st.log[:cst[i].log_len]
+            keys = log[st.in_budget[log]]                 # == list(budget[source_type].keys()): insertion order, popped ids gone
+            if sampled_number > len(keys):
+                sampled_ids = np.arange(len(keys))
+            else:
+                score = st.score[keys] ** 2
+                score = score / np.sum(score)
+                sampled_ids = np.random.choice(len(score), sampled_number, p=score, replace=False)
+            sampled_keys = np.ascontiguousarray(keys[sampled_ids])
+            tms = np.ascontiguousarray(st.b_time[sampled_keys])
+            touch_layer(i)                                # data.py:166-167 (ids are new to the layer and distinct)
+            st.ser[sampled_keys] = len(st.layer_ids) + np.arange(sampled_keys.shape[0])
+            st.in_layer[sampled_keys] = True
+            st.layer_time[sampled_keys] = tms
+            st.layer_ids.extend(sampled_keys.tolist())
+            add_budget(i, sampled_keys, tms)              # data.py:168-170
+            st.in_budget[sampled_keys] = False            # budget[source_type].pop(k)
+
+    states = {fg.types[i]: sts[i] for i in range(T) if sts[i] is not None}
+    layer_order = [fg.types[i] for i in sorted((i for i in range(T) if cst[i].layer_seq >= 0),
+                                               key=lambda i: cst[i].layer_seq)]
+    return _finish(fg, states, layer_order, feature_extractor)
+
+
+def _sample_slices(fg, time_range, sampled_depth, sampled_number, inp, feature_extractor):
+    """The same process with one (optionally native) budget update per adjacency slice — used when the library does not
+    export the batched entry point, and kept as a second implementation the tests compare with."""
     ref_graph = fg.graph
     max_time = np.max(list(time_range.keys()))
     states = {}                       # per type arrays
@@ -276,6 +457,12 @@ def sample_subgraph(graph, time_range, sampled_depth=2, sampled_number=8, inp=No
                 add_budget(source_type, int(k), int(st.b_time[k]))
                 st.in_budget[k] = False                   # budget[source_type].pop(k)
 
+    return _finish(fg, states, layer_order, feature_extractor)
+
+
+def _finish(fg, states, layer_order, feature_extractor):
+    """layer_data -> features (data.py:174) and the sampled adjacency (data.py:181-209)."""
+    ref_graph = fg.graph
     # hand the reference-shaped layer_data to the feature extractor (data.py:174)
     layer_data = defaultdict(lambda: {})
     for _type in layer_order:

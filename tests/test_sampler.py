@@ -44,7 +44,20 @@ class _GraphStub:
         return self._m
 
 
-def test_sampler_reproduces_reference_golden():
+@pytest.fixture(params=["batched", "slices", "numpy"])
+def sampler_impl(request, monkeypatch):
+    """The three code paths of sampler.py: whole add_budget batches in native code (default), one native call per
+    adjacency slice, pure numpy (library absent).  All must reproduce the reference bit for bit."""
+    if request.param != "batched":
+        monkeypatch.setattr(sampler, "_NATIVE_BATCH", [None, True])
+    if request.param == "numpy":
+        monkeypatch.setattr(sampler, "_NATIVE", [None, True])
+    if request.param == "batched" and sampler._native_batch() is None:
+        pytest.skip("libhgt_b200.so not built")
+    return request.param
+
+
+def test_sampler_reproduces_reference_golden(sampler_impl):
     fx = load_golden("sampler")
     g = _GraphStub(fx)
     fg = sampler.FrozenGraph(g)
@@ -68,7 +81,7 @@ def test_sampler_reproduces_reference_golden():
 
 
 @pytest.mark.skipif(not pyg_shim.reference_available(), reason="reference tree only exists in the dev container")
-def test_sampler_matches_live_reference_on_a_larger_graph_and_is_faster():
+def test_sampler_matches_live_reference_on_a_larger_graph_and_is_faster(sampler_impl):
     import time
     from oracle import make_golden as mg
     data = pyg_shim.load_reference_data()
@@ -103,3 +116,38 @@ def test_frozen_graph_from_plain_graph_argument():
     np.random.seed(case["np_seed"])
     out = sampler.sample_subgraph(g, fx["time_range"], case["depth"], case["number"], fx["inp"], _extractor)
     assert all(np.array_equal(out[3][k], case["indxs"][k]) for k in case["indxs"])
+
+
+def _run_both(g, fx, inp):
+    outs = []
+    for impl in ("active", "slices"):
+        saved = sampler._NATIVE_BATCH[:]
+        if impl == "slices":
+            sampler._NATIVE_BATCH[:] = [None, True]
+        try:
+            np.random.seed(21)
+            out = sampler.sample_subgraph(sampler.FrozenGraph(g), fx["time_range"], 2, 8, inp, _extractor)
+            outs.append((out, np.random.get_state()[1].copy()))
+        finally:
+            sampler._NATIVE_BATCH[:] = saved
+    (a, rng_a), (b, rng_b) = outs
+    assert np.array_equal(rng_a, rng_b)
+    assert list(a[3].keys()) == list(b[3].keys()) and all(np.array_equal(a[3][k], b[3][k]) for k in a[3])
+    na, nb = _norm(a[2]), _norm(b[2])
+    assert [x[:3] for x in na] == [x[:3] for x in nb] and all(np.array_equal(x[3], y[3]) for x, y in zip(na, nb))
+    return a
+
+
+def test_seed_ids_beyond_the_graph_and_unknown_seed_types():
+    """Seeds the frozen graph has never seen (an id past every adjacency, a type without edges) become isolated sampled
+    nodes, as in the reference (`graph.edge_list[_type]` is a defaultdict): the batched native path (which grows its
+    state arrays / hands unknown types to the per-slice path) agrees with the per-slice implementation."""
+    fx = load_golden("sampler")
+    g = _GraphStub(fx)
+    first = next(iter(fx["inp"]))
+    big = max(sampler.FrozenGraph(g).n_ids.values()) + 7
+    seeds = np.concatenate([np.asarray(fx["inp"][first]), [[big, 2010]]])
+    a = _run_both(g, fx, {first: seeds})
+    assert big in a[3][first].tolist()
+    a = _run_both(g, fx, {first: seeds, "never_seen_type": np.array([[3, 2011]])})
+    assert big in a[3][first].tolist() and a[3]["never_seen_type"].tolist() == [3]
