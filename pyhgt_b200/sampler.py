@@ -23,6 +23,7 @@ builds Python lists of pairs with the same content and order); ``pyhgt_b200.data
 """
 import ctypes as _c
 from collections import defaultdict
+from itertools import chain as _chain
 
 import numpy as np
 
@@ -45,27 +46,23 @@ class _Block:
     __slots__ = ("row_of", "ptr", "nbr", "time", "has_none", "nbr_addr", "time_addr", "ptr_list", "row_list")
 
     def __init__(self, tesr, n_target_ids):
-        keys = list(tesr.keys())
+        adls = list(tesr.values())
+        n_keys = len(adls)
         self.row_of = np.full(n_target_ids, -1, dtype=np.int64)
-        counts = np.fromiter((len(tesr[k]) for k in keys), dtype=np.int64, count=len(keys))
+        counts = np.fromiter(map(len, adls), dtype=np.int64, count=n_keys)
         self.ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        if keys:
-            self.row_of[np.asarray(keys, dtype=np.int64)] = np.arange(len(keys), dtype=np.int64)
+        if n_keys:
+            self.row_of[np.fromiter(tesr.keys(), dtype=np.int64, count=n_keys)] = np.arange(n_keys, dtype=np.int64)
         total = int(self.ptr[-1])
-        self.nbr = np.empty(total, dtype=np.int64)
-        self.time = np.empty(total, dtype=np.int64)
+        # one pass over the whole block (iterating a dict yields its keys = the neighbour ids, in insertion order)
+        self.nbr = np.fromiter(_chain.from_iterable(adls), dtype=np.int64, count=total)
         has_none = False
-        pos = 0
-        for k in keys:
-            adl = tesr[k]
-            n = len(adl)
-            self.nbr[pos:pos + n] = np.fromiter(adl.keys(), dtype=np.int64, count=n)
-            vals = list(adl.values())
-            if any(v is None for v in vals):
-                has_none = True
-                vals = [_NO_TIME if v is None else v for v in vals]
-            self.time[pos:pos + n] = np.asarray(vals, dtype=np.int64)
-            pos += n
+        try:
+            self.time = np.fromiter(_chain.from_iterable(map(dict.values, adls)), dtype=np.int64, count=total)
+        except TypeError:                                  # some edge times are None (data.py:125-126)
+            has_none = True
+            self.time = np.fromiter((_NO_TIME if v is None else v for adl in adls for v in adl.values()),
+                                    dtype=np.int64, count=total)
         self.has_none = has_none
         self.nbr_addr = self.nbr.ctypes.data               # base addresses for the native budget update
         self.time_addr = self.time.ctypes.data
@@ -88,22 +85,18 @@ class FrozenGraph:
         for t_t, d1 in graph.edge_list.items():
             for s_t, d2 in d1.items():
                 for r, tesr in d2.items():
-                    for tid, adl in tesr.items():
-                        if tid + 1 > n_ids[t_t]:
-                            n_ids[t_t] = tid + 1
-                        if adl:
-                            m = max(adl.keys()) + 1
-                            if m > n_ids[s_t]:
-                                n_ids[s_t] = m
-        self.n_ids = dict(n_ids)
+                    if tesr:
+                        n_ids[t_t] = max(n_ids[t_t], max(tesr.keys()) + 1)
         self.blocks = {}                                  # target_type -> source_type -> relation -> _Block (ordered)
         for t_t, d1 in graph.edge_list.items():
             self.blocks[t_t] = {}
             for s_t, d2 in d1.items():
                 self.blocks[t_t][s_t] = {}
                 for r, tesr in d2.items():
-                    self.blocks[t_t][s_t][r] = _Block(tesr, self.n_ids.get(t_t, 0))
-
+                    blk = self.blocks[t_t][s_t][r] = _Block(tesr, n_ids.get(t_t, 0))
+                    if blk.nbr.size:
+                        n_ids[s_t] = max(n_ids[s_t], int(blk.nbr.max()) + 1)
+        self.n_ids = dict(n_ids)
         self.types = []                                   # every type that occurs, targets first (index = native state slot)
         for t_t, d1 in graph.edge_list.items():
             for ty in [t_t] + list(d1.keys()):
